@@ -1,0 +1,372 @@
+// C ABI (include/hagrid_b200.h) over the `namespace hagrid` C++ API.
+//
+// This file only uses what the reference's own front end uses
+// (src/main.cpp:471-533: MemManager, Grid, the five build stages,
+// setup_traversal/traverse_grid and profile()), so it builds unchanged against
+//   * this repository's headers + kernels  -> libhagrid_b200.so  (the product)
+//   * /root/reference/src headers + objects -> oracle/_ref/libhagrid_ref.so
+//     (with -DHGB_REFERENCE_BUILD; test oracle and reference bench arm only).
+// Host-only translation unit: compiled with g++ -DHOST= -DDEVICE= exactly like
+// the reference compiles main.cpp (src/CMakeLists.txt:41-43).
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime_api.h>
+
+#include "build.h"
+#include "traverse.h"
+#include "mem_manager.h"
+
+#include "hagrid_b200.h"
+
+namespace hagrid {
+#ifdef HGB_REFERENCE_BUILD
+// Second build of the reference's traverse.cu with the `hit.id = steps` line
+// (src/traverse.cu:93) removed; see oracle/build_ref.sh.
+void setup_traversal_pid(const Grid& grid);
+void traverse_grid_pid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays);
+#else
+// Extra entry points of this library (hagrid_b200/include/hagrid/traverse.h).
+void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays);
+bool set_traversal_option(const char* key, int value);
+#endif
+}
+
+using namespace hagrid;
+
+struct hgb_scene {
+    MemManager mem;
+    Grid grid;
+    Tri* tris;
+    int num_tris;
+    int device;
+    Ray* frame_rays;
+    Hit* frame_hits;
+    int frame_capacity;
+
+    hgb_scene(int dev, bool keep)
+        : mem(keep), tris(nullptr), num_tris(0), device(dev),
+          frame_rays(nullptr), frame_hits(nullptr), frame_capacity(0)
+    {
+        grid.entries = nullptr;
+        grid.ref_ids = nullptr;
+        grid.cells = nullptr;
+        grid.small_cells = nullptr;
+        grid.num_cells = grid.num_entries = grid.num_refs = grid.shift = 0;
+        grid.dims = ivec3(0, 0, 0);
+        grid.bbox = BBox(vec3(0, 0, 0), vec3(0, 0, 0));
+    }
+};
+
+static thread_local std::string g_error;
+
+static int fail(const char* msg) {
+    g_error = msg;
+    return -1;
+}
+
+static bool bind(const hgb_scene* scene) {
+    if (!scene) { g_error = "null scene"; return false; }
+    if (cudaSetDevice(scene->device) != cudaSuccess) {
+        g_error = "cudaSetDevice failed";
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+
+static void release_grid(hgb_scene* s) {
+    // main.cpp:496-498 frees exactly these three; small_cells is leaked by the
+    // reference across rebuilds (build.cu:755). Freeing it here is harmless for
+    // both builds because it always comes from the same MemManager.
+    s->mem.free(s->grid.entries);
+    s->mem.free(s->grid.cells);
+    s->mem.free(s->grid.ref_ids);
+    s->mem.free(s->grid.small_cells);
+    s->grid.entries = nullptr;
+    s->grid.cells = nullptr;
+    s->grid.ref_ids = nullptr;
+    s->grid.small_cells = nullptr;
+}
+
+static void run_traverse(hgb_scene* s, const Ray* rays, Hit* hits, int n, int hit_mode) {
+    if (hit_mode == HGB_HIT_PRIM_ID) {
+#ifdef HGB_REFERENCE_BUILD
+        traverse_grid_pid(s->grid, s->tris, rays, hits, n);
+#else
+        traverse_grid_prim_ids(s->grid, s->tris, rays, hits, n);
+#endif
+    } else {
+        traverse_grid(s->grid, s->tris, rays, hits, n);
+    }
+}
+
+extern "C" {
+
+const char* hgb_impl(void) {
+#ifdef HGB_REFERENCE_BUILD
+    return "reference";
+#else
+    return "hagrid_b200";
+#endif
+}
+
+const char* hgb_last_error(void) { return g_error.c_str(); }
+
+int hgb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int hgb_set_option(const char* key, int value) {
+    if (!key) return fail("set_option: null key");
+#ifdef HGB_REFERENCE_BUILD
+    (void)value;
+    return 0;
+#else
+    return set_traversal_option(key, value) ? 0 : fail("set_option: unknown key");
+#endif
+}
+
+hgb_scene* hgb_scene_create(int device, int keep_alive) {
+    if (device < 0 || device >= hgb_device_count()) {
+        g_error = "no such CUDA device (this library has no CPU fallback)";
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { g_error = "cudaSetDevice failed"; return nullptr; }
+    return new hgb_scene(device, keep_alive != 0);
+}
+
+void hgb_scene_destroy(hgb_scene* s) {
+    if (!s) return;
+    if (bind(s)) {
+        cudaDeviceSynchronize();
+        release_grid(s);
+        s->mem.free(s->tris);
+        s->mem.free(s->frame_rays);
+        s->mem.free(s->frame_hits);
+    }
+    delete s;
+}
+
+int hgb_scene_set_tris(hgb_scene* s, const void* host_tris, int num_tris) {
+    if (!bind(s)) return -1;
+    if (!host_tris || num_tris <= 0) return fail("set_tris: empty triangle array");
+    s->mem.free(s->tris);
+    s->tris = s->mem.alloc<Tri>(num_tris);
+    s->mem.copy<Copy::HST_TO_DEV>(s->tris, static_cast<const Tri*>(host_tris), num_tris);
+    s->num_tris = num_tris;
+    return 0;
+}
+
+int hgb_scene_num_tris(const hgb_scene* s) { return s ? s->num_tris : 0; }
+size_t hgb_scene_peak_bytes(const hgb_scene* s) { return s ? s->mem.max_usage() : 0; }
+
+int hgb_build_grid(hgb_scene* s, float top_density, float snd_density) {
+    if (!bind(s)) return -1;
+    if (!s->tris) return fail("build_grid: no triangles");
+    release_grid(s);
+    build_grid(s->mem, s->tris, s->num_tris, s->grid, top_density, snd_density);
+    return 0;
+}
+
+int hgb_merge_grid(hgb_scene* s, float alpha) {
+    if (!bind(s)) return -1;
+    if (!s->grid.cells) return fail("merge_grid: no uncompressed grid");
+    merge_grid(s->mem, s->grid, alpha);
+    return 0;
+}
+
+int hgb_flatten_grid(hgb_scene* s) {
+    if (!bind(s)) return -1;
+    if (!s->grid.entries) return fail("flatten_grid: no grid");
+    flatten_grid(s->mem, s->grid);
+    return 0;
+}
+
+int hgb_expand_grid(hgb_scene* s, int iters) {
+    if (!bind(s)) return -1;
+    if (!s->grid.cells) return fail("expand_grid: no uncompressed grid");
+    expand_grid(s->mem, s->grid, s->tris, iters);
+    return 0;
+}
+
+int hgb_compress_grid(hgb_scene* s) {
+    if (!bind(s)) return -1;
+    if (!s->grid.cells) return fail("compress_grid: no uncompressed grid");
+    return compress_grid(s->mem, s->grid) ? 1 : 0;
+}
+
+int hgb_build_pipeline(hgb_scene* s, float top_density, float snd_density,
+                       float alpha, int exp_iters, int compress,
+                       int warmup, int iters, float* ms_out) {
+    if (!bind(s)) return -1;
+    if (!s->tris) return fail("build_pipeline: no triangles");
+    for (int i = 0; i < warmup + iters; i++) {
+        release_grid(s);
+        float ms = profile([&] {
+            build_grid(s->mem, s->tris, s->num_tris, s->grid, top_density, snd_density);
+            merge_grid(s->mem, s->grid, alpha);
+            flatten_grid(s->mem, s->grid);
+            expand_grid(s->mem, s->grid, s->tris, exp_iters);
+            if (compress) compress_grid(s->mem, s->grid);
+        });
+        if (i >= warmup && ms_out) ms_out[i - warmup] = ms;
+    }
+    return 0;
+}
+
+int hgb_setup_traversal(hgb_scene* s) {
+    if (!bind(s)) return -1;
+    if (!s->grid.entries) return fail("setup_traversal: no grid");
+    setup_traversal(s->grid);
+#ifdef HGB_REFERENCE_BUILD
+    setup_traversal_pid(s->grid);
+#endif
+    return 0;
+}
+
+int hgb_traverse_grid(hgb_scene* s, const void* dev_rays, void* dev_hits, int num_rays, int hit_mode) {
+    if (!bind(s)) return -1;
+    if (!s->grid.entries) return fail("traverse_grid: no grid");
+    if (num_rays <= 0) return 0;
+    run_traverse(s, static_cast<const Ray*>(dev_rays), static_cast<Hit*>(dev_hits), num_rays, hit_mode);
+    return 0;
+}
+
+int hgb_traverse_timed(hgb_scene* s, const void* dev_rays, void* dev_hits, int num_rays,
+                       int hit_mode, int warmup, int iters, float* ms_out) {
+    if (!bind(s)) return -1;
+    if (!s->grid.entries) return fail("traverse_timed: no grid");
+    if (num_rays <= 0) return fail("traverse_timed: no rays");
+    auto rays = static_cast<const Ray*>(dev_rays);
+    auto hits = static_cast<Hit*>(dev_hits);
+    for (int i = 0; i < warmup; i++) run_traverse(s, rays, hits, num_rays, hit_mode);
+    for (int i = 0; i < iters; i++) {
+        float ms = profile([&] { run_traverse(s, rays, hits, num_rays, hit_mode); });
+        if (ms_out) ms_out[i] = ms;
+    }
+    return 0;
+}
+
+int hgb_traverse_grid_host(hgb_scene* s, const void* host_rays, void* host_hits, int num_rays, int hit_mode) {
+    if (!bind(s)) return -1;
+    if (!s->grid.entries) return fail("traverse_grid_host: no grid");
+    if (num_rays <= 0) return 0;
+    if (num_rays > s->frame_capacity) {
+        s->mem.free(s->frame_rays);
+        s->mem.free(s->frame_hits);
+        s->frame_rays = s->mem.alloc<Ray>(num_rays);
+        s->frame_hits = s->mem.alloc<Hit>(num_rays);
+        s->frame_capacity = num_rays;
+    }
+    s->mem.copy<Copy::HST_TO_DEV>(s->frame_rays, static_cast<const Ray*>(host_rays), num_rays);
+    run_traverse(s, s->frame_rays, s->frame_hits, num_rays, hit_mode);
+    s->mem.copy<Copy::DEV_TO_HST>(static_cast<Hit*>(host_hits), s->frame_hits, num_rays);
+    return 0;
+}
+
+int hgb_grid_get_info(const hgb_scene* s, hgb_grid_info* info) {
+    if (!s || !info) return fail("grid_get_info: null argument");
+    const Grid& g = s->grid;
+    std::memset(info, 0, sizeof(*info));
+    info->bbox_min[0] = g.bbox.min.x; info->bbox_min[1] = g.bbox.min.y; info->bbox_min[2] = g.bbox.min.z;
+    info->bbox_max[0] = g.bbox.max.x; info->bbox_max[1] = g.bbox.max.y; info->bbox_max[2] = g.bbox.max.z;
+    info->dims[0] = g.dims.x; info->dims[1] = g.dims.y; info->dims[2] = g.dims.z;
+    info->shift = g.shift;
+    info->num_cells = g.num_cells;
+    info->num_entries = g.num_entries;
+    info->num_refs = g.num_refs;
+    info->compressed = g.small_cells ? 1 : 0;
+    if (g.offsets.size() > HGB_MAX_LEVELS) return fail("grid_get_info: too many levels");
+    info->num_offsets = static_cast<int32_t>(g.offsets.size());
+    for (size_t i = 0; i < g.offsets.size(); i++) info->offsets[i] = g.offsets[i];
+    return 0;
+}
+
+int hgb_grid_download(const hgb_scene* cs, int which, void* host_dst, size_t bytes) {
+    auto s = const_cast<hgb_scene*>(cs);
+    if (!bind(s)) return -1;
+    if (!host_dst) return fail("grid_download: null destination");
+    const Grid& g = s->grid;
+    const void* src = nullptr;
+    size_t have = 0;
+    switch (which) {
+        case HGB_ARRAY_ENTRIES:     src = g.entries;     have = size_t(g.num_entries) * sizeof(Entry); break;
+        case HGB_ARRAY_CELLS:       src = g.cells;       have = size_t(g.num_cells) * sizeof(Cell); break;
+        case HGB_ARRAY_SMALL_CELLS: src = g.small_cells; have = size_t(g.num_cells) * sizeof(SmallCell); break;
+        case HGB_ARRAY_REFS:        src = g.ref_ids;     have = size_t(g.num_refs) * sizeof(int); break;
+        case HGB_ARRAY_TRIS:        src = s->tris;       have = size_t(s->num_tris) * sizeof(Tri); break;
+        default: return fail("grid_download: unknown array");
+    }
+    if (!src) return fail("grid_download: array not present");
+    if (bytes != have) return fail("grid_download: size mismatch");
+    if (bytes) s->mem.copy<Copy::DEV_TO_HST>(static_cast<char*>(host_dst), static_cast<const char*>(src), bytes);
+    return 0;
+}
+
+int hgb_grid_upload(hgb_scene* s, const hgb_grid_info* info,
+                    const void* host_entries, const void* host_cells, const void* host_refs) {
+    if (!bind(s)) return -1;
+    if (!info || !host_entries || !host_cells) return fail("grid_upload: null argument");
+    if (info->num_offsets < 0 || info->num_offsets > HGB_MAX_LEVELS) return fail("grid_upload: bad offsets");
+    release_grid(s);
+    Grid& g = s->grid;
+    g.bbox = BBox(vec3(info->bbox_min[0], info->bbox_min[1], info->bbox_min[2]),
+                  vec3(info->bbox_max[0], info->bbox_max[1], info->bbox_max[2]));
+    g.dims = ivec3(info->dims[0], info->dims[1], info->dims[2]);
+    g.shift = info->shift;
+    g.num_cells = info->num_cells;
+    g.num_entries = info->num_entries;
+    g.num_refs = info->num_refs;
+    g.offsets.assign(info->offsets, info->offsets + info->num_offsets);
+
+    g.entries = s->mem.alloc<Entry>(g.num_entries);
+    s->mem.copy<Copy::HST_TO_DEV>(g.entries, static_cast<const Entry*>(host_entries), g.num_entries);
+    // One spare element so an empty reference array still owns a slot.
+    g.ref_ids = s->mem.alloc<int>(size_t(g.num_refs) + 1);
+    if (g.num_refs) {
+        if (!host_refs) return fail("grid_upload: null reference array");
+        s->mem.copy<Copy::HST_TO_DEV>(g.ref_ids, static_cast<const int*>(host_refs), g.num_refs);
+    }
+    if (info->compressed) {
+        g.small_cells = s->mem.alloc<SmallCell>(g.num_cells);
+        s->mem.copy<Copy::HST_TO_DEV>(g.small_cells, static_cast<const SmallCell*>(host_cells), g.num_cells);
+    } else {
+        g.cells = s->mem.alloc<Cell>(g.num_cells);
+        s->mem.copy<Copy::HST_TO_DEV>(g.cells, static_cast<const Cell*>(host_cells), g.num_cells);
+    }
+    return 0;
+}
+
+void* hgb_device_alloc(hgb_scene* s, size_t bytes) {
+    if (!bind(s) || bytes == 0) return nullptr;
+    return s->mem.alloc<char>(bytes);
+}
+
+void hgb_device_free(hgb_scene* s, void* dev_ptr) {
+    if (!bind(s) || !dev_ptr) return;
+    s->mem.free(static_cast<char*>(dev_ptr));
+}
+
+int hgb_copy_to_device(hgb_scene* s, void* dev_dst, const void* host_src, size_t bytes) {
+    if (!bind(s)) return -1;
+    if (bytes) s->mem.copy<Copy::HST_TO_DEV>(static_cast<char*>(dev_dst), static_cast<const char*>(host_src), bytes);
+    return 0;
+}
+
+int hgb_copy_to_host(hgb_scene* s, void* host_dst, const void* dev_src, size_t bytes) {
+    if (!bind(s)) return -1;
+    if (bytes) s->mem.copy<Copy::DEV_TO_HST>(static_cast<char*>(host_dst), static_cast<const char*>(dev_src), bytes);
+    return 0;
+}
+
+int hgb_device_synchronize(void) {
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : fail("cudaDeviceSynchronize failed");
+}
+
+} // extern "C"

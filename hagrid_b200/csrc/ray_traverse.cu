@@ -1,0 +1,379 @@
+// Traversal of the irregular grid for sm_100a: setup_traversal / traverse_grid
+// (API of src/traverse.h:11-14; semantics of src/traverse.cu:28-95).
+//
+// Per-ray semantics are exactly the reference's: the same cells are visited in
+// the same order, the references of a cell are tested in array order with the
+// shrinking tmax, and the ray stops when `hit.t <= texit` or the voxel leaves
+// the grid. What is different is how rays are mapped onto the machine:
+//
+//   * persistent warps (one resident grid sized to the SM count) pull rays
+//     from a global counter, so a lane whose ray ends is refilled instead of
+//     idling until the slowest ray of its warp finishes;
+//   * the cell walk and the ray/triangle tests are two separate warp phases.
+//     Lanes that reach a non-empty cell park their reference range; the warp
+//     keeps stepping the other lanes through (mostly empty) cells and only
+//     then runs the triangle phase with most lanes busy, one triangle per lane
+//     per iteration, until too few lanes have work left (`__ballot_sync`
+//     population counts drive the phase changes).
+//
+// The grid, the references and the triangles (tens of MB) live in the 126 MB
+// L2; compulsory HBM traffic is 32 B/ray in + 16 B/hit out.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "device_math.cuh"
+#include "runtime.h"
+#include "traverse.h"
+
+namespace hagrid {
+
+namespace {
+
+/// Grid constants captured by setup_traversal (src/traverse.cu:97-108). All
+/// floating-point values are computed on the host in IEEE arithmetic.
+struct TraversalParams {
+    int   dims_x, dims_y, dims_z;       // virtual dims = top dims << shift
+    int   top_x, top_y;                 // top-level dims (x, y)
+    int   shift;
+    float min_x, min_y, min_z;          // grid box
+    float max_x, max_y, max_z;
+    float cell_x, cell_y, cell_z;       // extents / virtual dims
+    float inv_x, inv_y, inv_z;          // virtual dims / extents
+};
+
+TraversalParams g_params;
+bool g_params_set = false;
+
+struct RayState {
+    float ox, oy, oz, tmin;
+    float dx, dy, dz;
+    float ix, iy, iz;                   // safe_rcp(dir)
+    float hit_t;
+    int   hit_id;
+    int   steps;
+    int   vx, vy, vz;                   // current voxel
+};
+
+/// Ray/triangle test, expression shapes as in the reference SASS:
+///   c   = v0 - org                                    FADD x3
+///   r   = dir x c      r.x = fma(dy, cz, -(dz*cy)) .. FMUL+FFMA x3
+///   det = fma(nz, dz, fma(nx, dx, ny*dy))             FMUL+FFMA x2
+///   u,v = prodsign(dot(r, e2 | e1), det)  w = (|det| - u) - v
+///   t   = prodsign(dot(n, c), det)
+///   accept: u,v,w >= -1e-9,  t >= |det|*tmin,  |det|*tmax > t ; hit.t = t * rcp(|det|)
+/// (src/prims.h:266-295)
+__device__ __forceinline__ void intersect_tri(RayState& r, const Tri* __restrict__ tris, int ref) {
+    using namespace dev;
+    const float4 t0 = ldg4(reinterpret_cast<const float4*>(tris + ref) + 0);   // v0, nx
+    const float4 t1 = ldg4(reinterpret_cast<const float4*>(tris + ref) + 1);   // e1, ny
+    const float4 t2 = ldg4(reinterpret_cast<const float4*>(tris + ref) + 2);   // e2, nz
+    const float cx = sub(t0.x, r.ox), cy = sub(t0.y, r.oy), cz = sub(t0.z, r.oz);
+    const float rx = diff_of_products(r.dy, cz, r.dz, cy);
+    const float ry = diff_of_products(r.dz, cx, r.dx, cz);
+    const float rz = diff_of_products(r.dx, cy, r.dy, cx);
+    const float det = dot3(t0.w, t1.w, t2.w, r.dx, r.dy, r.dz);
+    const float abs_det = fabsf(det);
+    const float u = prodsign(dot3(rx, ry, rz, t2.x, t2.y, t2.z), det);
+    const float v = prodsign(dot3(rx, ry, rz, t1.x, t1.y, t1.z), det);
+    const float w = sub(sub(abs_det, u), v);
+    const float eps = 1e-9f;
+    if (u >= -eps && v >= -eps && w >= -eps) {
+        const float t = prodsign(dot3(t0.w, t1.w, t2.w, cx, cy, cz), det);
+        if (t >= mul(abs_det, r.tmin) && mul(abs_det, r.hit_t) > t) {
+            r.hit_t = mul(t, rcp(abs_det));
+            r.hit_id = ref;
+        }
+    }
+}
+
+/// Loads ray `id`, clips it against the grid box and finds its first voxel
+/// (src/traverse.cu:36-54). Returns false when the ray misses the grid.
+__device__ __forceinline__ bool start_ray(RayState& r, const TraversalParams& P, const Ray* __restrict__ rays, int id) {
+    using namespace dev;
+    const float4 a = ldg4(reinterpret_cast<const float4*>(rays + id) + 0);
+    const float4 b = ldg4(reinterpret_cast<const float4*>(rays + id) + 1);
+    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tmin = a.w;
+    r.dx = b.x; r.dy = b.y; r.dz = b.z;
+    r.ix = safe_rcp(b.x); r.iy = safe_rcp(b.y); r.iz = safe_rcp(b.z);
+    r.hit_t = b.w;
+    r.hit_id = -1;
+    r.steps = 0;
+
+    const float lx = mul(sub(P.min_x, r.ox), r.ix), hx = mul(sub(P.max_x, r.ox), r.ix);
+    const float ly = mul(sub(P.min_y, r.oy), r.iy), hy = mul(sub(P.max_y, r.oy), r.iy);
+    const float lz = mul(sub(P.min_z, r.oz), r.iz), hz = mul(sub(P.max_z, r.oz), r.iz);
+    const float t0 = fmaxf(sel_min(lx, hx), fmaxf(sel_min(ly, hy), sel_min(lz, hz)));
+    const float t1 = fminf(sel_max(lx, hx), fminf(sel_max(ly, hy), sel_max(lz, hz)));
+    const float tstart = fmaxf(t0, r.tmin);
+    const float tend = fminf(t1, b.w);
+    if (tstart > tend) return false;
+
+    // voxel = clamp(int((t * dir + org - grid_min) * grid_inv), 0, dims - 1):  FFMA, FADD, FMUL, F2I
+    r.vx = min(P.dims_x - 1, max(0, trunc_to_int(mul(sub(fma(r.dx, tstart, r.ox), P.min_x), P.inv_x))));
+    r.vy = min(P.dims_y - 1, max(0, trunc_to_int(mul(sub(fma(r.dy, tstart, r.oy), P.min_y), P.inv_y))));
+    r.vz = min(P.dims_z - 1, max(0, trunc_to_int(mul(sub(fma(r.dz, tstart, r.oz), P.min_z), P.inv_z))));
+    return true;
+}
+
+/// Enters the cell owning the current voxel, computes where the ray leaves it
+/// and moves `voxel` to the next cell (src/traverse.cu:57-77). Returns the
+/// exit distance; `cell` receives the reference range.
+template <typename CellT>
+__device__ __forceinline__ float enter_cell(RayState& r, const TraversalParams& P,
+                                            const uint32_t* __restrict__ entries,
+                                            const CellT* __restrict__ cells, dev::CellBox& cell) {
+    using namespace dev;
+    const int cell_id = lookup_cell(entries, P.shift, P.top_x, P.top_y, r.vx, r.vy, r.vz);
+    cell = load_cell_box(cells, cell_id);
+
+    const bool px = r.dx >= 0.0f, py = r.dy >= 0.0f, pz = r.dz >= 0.0f;
+    const int cx = px ? cell.max_x : cell.min_x;
+    const int cy = py ? cell.max_y : cell.min_y;
+    const int cz = pz ? cell.max_z : cell.min_z;
+    // tcell = (cell_point * cell_size + grid_min - org) * inv_dir:  I2F, FFMA, FADD, FMUL
+    const float tx = mul(sub(fma(int_to_float(cx), P.cell_x, P.min_x), r.ox), r.ix);
+    const float ty = mul(sub(fma(int_to_float(cy), P.cell_y, P.min_y), r.oy), r.iy);
+    const float tz = mul(sub(fma(int_to_float(cz), P.cell_z, P.min_z), r.oz), r.iz);
+    const float texit = fminf(tx, fminf(ty, tz));
+
+    // On the exit axis step across the exact integer plane, elsewhere re-derive the voxel from texit
+    const int ex = trunc_to_int(mul(sub(fma(r.dx, texit, r.ox), P.min_x), P.inv_x));
+    const int ey = trunc_to_int(mul(sub(fma(r.dy, texit, r.oy), P.min_y), P.inv_y));
+    const int ez = trunc_to_int(mul(sub(fma(r.dz, texit, r.oz), P.min_z), P.inv_z));
+    const int nx = texit == tx ? cx + (px ? 0 : -1) : ex;
+    const int ny = texit == ty ? cy + (py ? 0 : -1) : ey;
+    const int nz = texit == tz ? cz + (pz ? 0 : -1) : ez;
+    r.vx = px ? max(nx, r.vx) : min(nx, r.vx);
+    r.vy = py ? max(ny, r.vy) : min(ny, r.vy);
+    r.vz = pz ? max(nz, r.vz) : min(nz, r.vz);
+    return texit;
+}
+
+__device__ __forceinline__ bool outside(const RayState& r, const TraversalParams& P) {
+    return (r.vx < 0) | (r.vx >= P.dims_x) | (r.vy < 0) | (r.vy >= P.dims_y) | (r.vz < 0) | (r.vz >= P.dims_z);
+}
+
+template <bool kPrimId>
+__device__ __forceinline__ void finish_ray(const RayState& r, Hit* __restrict__ hits, int id) {
+    // u = v = 0: the reference never defines COMPUTE_UVS (src/prims.h:285-288)
+    *reinterpret_cast<float4*>(hits + id) =
+        make_float4(__int_as_float(kPrimId ? r.hit_id : r.steps), r.hit_t, 0.0f, 0.0f);
+}
+
+// ---------------------------------------------------------------------------
+// Variant 0: one thread per ray (the reference's mapping), kept as the
+// in-library baseline that the scheduled kernel is measured against.
+// ---------------------------------------------------------------------------
+template <typename CellT, bool kPrimId>
+__global__ void __launch_bounds__(128)
+traverse_per_thread(const __grid_constant__ TraversalParams P,
+                    const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
+                    const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
+                    const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays) {
+    constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
+    const int id = threadIdx.x + blockDim.x * blockIdx.x;
+    if (id >= num_rays) return;
+    RayState r;
+    if (start_ray(r, P, rays, id)) {
+        while (true) {
+            dev::CellBox cell;
+            const float texit = enter_cell(r, P, entries, cells, cell);
+            if (kSentinel) {
+                int cur = cell.begin;
+                int ref = cur >= 0 ? __ldg(ref_ids + cur++) : -1;
+                while (ref >= 0) {
+                    const int next = __ldg(ref_ids + cur++);
+                    intersect_tri(r, tris, ref);
+                    ref = next;
+                }
+                r.steps += 1 + (cur - cell.begin);
+            } else {
+                int cur = cell.begin;
+                int ref = cur < cell.end ? __ldg(ref_ids + cur++) : -1;
+                while (ref >= 0) {
+                    const int next = cur < cell.end ? __ldg(ref_ids + cur++) : -1;
+                    intersect_tri(r, tris, ref);
+                    ref = next;
+                }
+                r.steps += 1 + (cell.end - cell.begin);
+            }
+            if (r.hit_t <= texit || outside(r, P)) break;
+        }
+    }
+    finish_ray<kPrimId>(r, hits, id);
+}
+
+// ---------------------------------------------------------------------------
+// Variant 1: persistent warps, phase-scheduled (see the header comment).
+// ---------------------------------------------------------------------------
+constexpr int kBlockThreads = 128;
+constexpr int kTriPhaseMinLanes = 12;   // leave the triangle phase when fewer lanes have work
+constexpr int kRefillMinLanes   = 8;    // fetch new rays when at least this many lanes are idle
+
+template <typename CellT, bool kPrimId>
+__global__ void __launch_bounds__(kBlockThreads)
+traverse_persistent(const __grid_constant__ TraversalParams P,
+                    const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
+                    const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
+                    const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
+                    int* __restrict__ next_ray) {
+    constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
+    constexpr unsigned kAll = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+
+    RayState r;
+    int   ray_id = -1;          // -1: lane is idle
+    int   ref = -1;             // reference being tested next (-1: none parked)
+    int   cur = 0, end = 0;     // rest of the parked reference range
+    float texit = 0.0f;
+    bool  drained = false;      // the global ray counter ran out
+
+    while (true) {
+        // ---- refill idle lanes from the global counter
+        const unsigned idle = __ballot_sync(kAll, ray_id < 0);
+        if (idle == kAll && drained) break;
+        if (!drained && __popc(idle) >= kRefillMinLanes) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(next_ray, __popc(idle));
+            base = __shfl_sync(kAll, base, 0);
+            if (base >= num_rays) drained = true;
+            if (ray_id < 0) {
+                const int id = base + __popc(idle & ((1u << lane) - 1u));
+                if (id < num_rays) {
+                    if (start_ray(r, P, rays, id)) ray_id = id;
+                    else finish_ray<kPrimId>(r, hits, id);
+                }
+            }
+        }
+
+        // ---- cell phase: every lane without parked references walks on
+        while (__any_sync(kAll, ray_id >= 0 && ref < 0)) {
+            if (ray_id >= 0 && ref < 0) {
+                dev::CellBox cell;
+                texit = enter_cell(r, P, entries, cells, cell);
+                cur = cell.begin;
+                if (kSentinel) {
+                    ref = cur >= 0 ? __ldg(ref_ids + cur++) : -1;
+                    r.steps += 1 + (ref >= 0 ? 1 : 0);      // +1 per reference word read, sentinel included
+                } else {
+                    end = cell.end;
+                    ref = cur < end ? __ldg(ref_ids + cur++) : -1;
+                    r.steps += 1 + (cell.end - cell.begin);
+                }
+                if (ref < 0 && (r.hit_t <= texit || outside(r, P))) {
+                    finish_ray<kPrimId>(r, hits, ray_id);
+                    ray_id = -1;
+                }
+            }
+        }
+
+        // ---- triangle phase: one triangle per busy lane per iteration
+        unsigned busy = __ballot_sync(kAll, ref >= 0);
+        while (busy) {
+            if (ref >= 0) {
+                int next;
+                if (kSentinel) { next = __ldg(ref_ids + cur++); r.steps++; }
+                else           { next = cur < end ? __ldg(ref_ids + cur++) : -1; }
+                intersect_tri(r, tris, ref);
+                ref = next;
+                if (ref < 0 && (r.hit_t <= texit || outside(r, P))) {
+                    finish_ray<kPrimId>(r, hits, ray_id);
+                    ray_id = -1;
+                }
+            }
+            busy = __ballot_sync(kAll, ref >= 0);
+            if (__popc(busy) < kTriPhaseMinLanes) break;
+        }
+    }
+}
+
+int* g_ray_counter[16] = {};
+
+int* ray_counter() {
+    int dev = 0;
+    HGB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) { std::fprintf(stderr, "hagrid_b200: device index out of range\n"); std::abort(); }
+    if (!g_ray_counter[dev]) HGB_CUDA(cudaMalloc(&g_ray_counter[dev], 64));
+    return g_ray_counter[dev];
+}
+
+int g_variant = -1;
+
+int traverse_variant() {
+    if (g_variant < 0) {
+        const char* v = std::getenv("HGB_TRAVERSE_VARIANT");
+        g_variant = v ? std::atoi(v) : 1;
+    }
+    return g_variant;
+}
+
+template <typename CellT, bool kPrimId>
+void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
+    if (num_rays <= 0) return;
+    if (!g_params_set) {
+        std::fprintf(stderr, "hagrid_b200: traverse_grid called before setup_traversal\n");
+        std::abort();
+    }
+    auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
+    if (traverse_variant() == 0) {
+        traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128>>>(
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays);
+    } else {
+        static int blocks_per_sm = 0, num_sms = 0;
+        if (!num_sms) {
+            int dev = 0;
+            HGB_CUDA(cudaGetDevice(&dev));
+            HGB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        int occ = 0;
+        HGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traverse_persistent<CellT, kPrimId>, kBlockThreads, 0));
+        blocks_per_sm = occ > 0 ? occ : 1;
+        int* counter = ray_counter();
+        HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), 0));
+        const int blocks = min(num_sms * blocks_per_sm, round_div(num_rays, kBlockThreads));
+        traverse_persistent<CellT, kPrimId><<<blocks, kBlockThreads>>>(
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, counter);
+    }
+    HGB_CUDA(cudaGetLastError());
+}
+
+template <bool kPrimId>
+void dispatch(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
+    if (grid.small_cells) launch<SmallCell, kPrimId>(grid, grid.small_cells, tris, rays, hits, num_rays);
+    else                  launch<Cell, kPrimId>(grid, grid.cells, tris, rays, hits, num_rays);
+}
+
+} // namespace
+
+void setup_traversal(const Grid& grid) {
+    // Host IEEE arithmetic, same expressions as src/traverse.cu:97-101.
+    const vec3 extents = grid.bbox.extents();
+    const ivec3 dims = grid.dims << grid.shift;
+    const vec3 inv = vec3(dims) / extents;
+    const vec3 cell = extents / vec3(dims);
+    TraversalParams& P = g_params;
+    P.dims_x = dims.x; P.dims_y = dims.y; P.dims_z = dims.z;
+    P.top_x = dims.x >> grid.shift; P.top_y = dims.y >> grid.shift;
+    P.shift = grid.shift;
+    P.min_x = grid.bbox.min.x; P.min_y = grid.bbox.min.y; P.min_z = grid.bbox.min.z;
+    P.max_x = grid.bbox.max.x; P.max_y = grid.bbox.max.y; P.max_z = grid.bbox.max.z;
+    P.cell_x = cell.x; P.cell_y = cell.y; P.cell_z = cell.z;
+    P.inv_x = inv.x; P.inv_y = inv.y; P.inv_z = inv.z;
+    g_params_set = true;
+}
+
+bool set_traversal_option(const char* key, int value) {
+    if (!std::strcmp(key, "traverse_variant")) { g_variant = value; return true; }
+    return false;
+}
+
+void traverse_grid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
+    dispatch<false>(grid, tris, rays, hits, num_rays);
+}
+
+void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
+    dispatch<true>(grid, tris, rays, hits, num_rays);
+}
+
+} // namespace hagrid

@@ -1,0 +1,114 @@
+// Runtime support of the path: the device buffer pool behind MemManager
+// (interface of src/mem_manager.h:34-119) and the device timer profile()
+// (src/profile.cu:5-18).
+#include <algorithm>
+#include <iostream>
+
+#include "mem_manager.h"
+#include "runtime.h"
+
+namespace hagrid {
+
+namespace {
+
+/// Stream-ordered allocation on the legacy default stream: the pool keeps
+/// released memory (unlimited release threshold), so growing and shrinking
+/// slots costs no cudaMalloc/cudaFree device synchronisation after warm-up.
+void prepare_pool() {
+    static bool done[64] = {};
+    int dev = 0;
+    HGB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    HGB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long threshold = ~0ull;
+    HGB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    done[dev] = true;
+}
+
+void release(Slot& slot) {
+    if (slot.ptr) HGB_CUDA(cudaFreeAsync(slot.ptr, 0));
+    slot.ptr = nullptr;
+    slot.size = 0;
+}
+
+} // namespace
+
+void MemManager::alloc_slot(Slot& slot, size_t bytes) {
+    if (slot.in_use) {
+        std::cerr << "MemManager: slot handed out twice" << std::endl;
+        std::abort();
+    }
+    if (slot.size < bytes || !slot.ptr) {
+        prepare_pool();
+        const size_t old = slot.size;
+        release(slot);
+        // Zero-byte requests still get a distinct address so that free() can track them.
+        HGB_CUDA(cudaMallocAsync(&slot.ptr, std::max<size_t>(bytes, 16), 0));
+        slot.size = bytes;
+        usage_ += bytes - old;
+        max_usage_ = std::max(max_usage_, usage_);
+    }
+    slot.in_use = true;
+
+    // keep mode: when the pool is at its high-water mark, give one idle slot
+    // back so that retained buffers cannot grow without bound (mem_manager.cu:36-44).
+    if (keep_ && usage_ >= max_usage_) {
+        for (auto& other : slots_) {
+            if (other.in_use || !other.ptr) continue;
+            usage_ -= other.size;
+            release(other);
+            break;
+        }
+    }
+}
+
+void MemManager::free_slot(Slot& slot) {
+    slot.in_use = false;
+    if (!keep_) {
+        usage_ -= slot.size;
+        release(slot);
+    }
+}
+
+void MemManager::copy_dev_to_dev(void* dst, const void* src, size_t bytes) {
+    HGB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+}
+
+void MemManager::copy_hst_to_dev(void* dst, const void* src, size_t bytes) {
+    HGB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+}
+
+void MemManager::copy_dev_to_hst(void* dst, const void* src, size_t bytes) {
+    HGB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+}
+
+void MemManager::zero_dev(void* ptr, size_t bytes) { HGB_CUDA(cudaMemsetAsync(ptr, 0x00, bytes, 0)); }
+void MemManager::one_dev(void* ptr, size_t bytes)  { HGB_CUDA(cudaMemsetAsync(ptr, 0xFF, bytes, 0)); }
+
+void MemManager::debug_slots() const {
+    size_t total = 0;
+    std::cout << "SLOTS: " << std::endl;
+    for (const Slot& slot : slots_) {
+        std::cout << (slot.in_use ? "[X] " : "[ ] ") << double(slot.size) / (1024.0 * 1024.0) << "MB" << std::endl;
+        total += slot.size;
+    }
+    std::cout << double(total) / (1024.0 * 1024.0) << "MB total" << std::endl;
+}
+
+float profile(std::function<void()> work) {
+    cudaEvent_t begin, end;
+    HGB_CUDA(cudaEventCreate(&begin));
+    HGB_CUDA(cudaEventCreate(&end));
+    HGB_CUDA(cudaEventRecord(begin, 0));
+    work();
+    HGB_CUDA(cudaEventRecord(end, 0));
+    HGB_CUDA(cudaEventSynchronize(end));
+    float ms = 0.0f;
+    HGB_CUDA(cudaEventElapsedTime(&ms, begin, end));
+    HGB_CUDA(cudaEventDestroy(begin));
+    HGB_CUDA(cudaEventDestroy(end));
+    return ms;
+}
+
+} // namespace hagrid

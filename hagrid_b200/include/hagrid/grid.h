@@ -1,0 +1,6 @@
+// Compatibility name: the reference front end includes "grid.h" (src/grid.h);
+// in this library every public type of the path lives in hgb_types.h.
+#ifndef GRID_H
+#define GRID_H
+#include "hgb_types.h"
+#endif

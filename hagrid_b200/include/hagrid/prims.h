@@ -1,0 +1,6 @@
+// Compatibility name: the reference front end includes "prims.h" (src/prims.h);
+// in this library every public type of the path lives in hgb_types.h.
+#ifndef PRIMITIVES_H
+#define PRIMITIVES_H
+#include "hgb_types.h"
+#endif

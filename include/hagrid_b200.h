@@ -1,0 +1,147 @@
+/* hagrid_b200 — C ABI of the B200-native irregular-grid build + traversal path.
+ *
+ * The reference (cg-saarland/hagrid) exposes this path as C++ symbols in
+ * `namespace hagrid` (src/build.h:17-31, src/traverse.h:11-14) driven by
+ * src/main.cpp.  There is no FFI in the reference; this header is the plain-C
+ * boundary a foreign host (ctypes, cgo, JNI ...) binds instead.  Every entry
+ * point cites the reference interface it stands for.  All pointers are raw
+ * host or device addresses, all sizes are element counts or bytes; no C++ or
+ * torch types cross this boundary.
+ *
+ * The same source that implements this ABI (hagrid_b200/csrc/c_api.cpp) also
+ * compiles, unchanged, against the reference's own headers and objects
+ * (oracle/build_ref.sh -> oracle/_ref/libhagrid_ref.so); that is how the
+ * parity tests drive the reference and this library through one interface.
+ *
+ * Error behaviour: the reference aborts the process on any CUDA error
+ * (src/common.h:101-108).  The C++ API of this library keeps that behaviour;
+ * the C ABI functions return 0 on success and a negative code on argument
+ * errors (the message is available from hgb_last_error()).
+ */
+#ifndef HAGRID_B200_H
+#define HAGRID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGB_MAX_LEVELS 32
+
+#if defined(__GNUC__)
+#define HGB_API __attribute__((visibility("default")))
+#else
+#define HGB_API
+#endif
+
+/* Opaque scene handle: one MemManager (src/mem_manager.h:34), one device Tri
+ * array (src/prims.h:13) and one Grid (src/grid.h:48), as main.cpp:471-478
+ * sets them up. */
+typedef struct hgb_scene hgb_scene;
+
+/* Host-visible part of `hagrid::Grid` (src/grid.h:48-62). */
+typedef struct hgb_grid_info {
+    float   bbox_min[3];
+    float   bbox_max[3];
+    int32_t dims[3];        /* top-level dimensions                         */
+    int32_t shift;          /* log2(virtual dims / top-level dims)          */
+    int32_t num_cells;
+    int32_t num_entries;
+    int32_t num_refs;
+    int32_t compressed;     /* 1 when small_cells != nullptr                */
+    int32_t num_offsets;
+    int32_t offsets[HGB_MAX_LEVELS];
+} hgb_grid_info;
+
+/* What traverse_grid stores in Hit::id. The reference kernel overwrites the
+ * primitive id with its step counter (src/traverse.cu:93); HGB_HIT_STEPS is
+ * that verbatim behaviour, HGB_HIT_PRIM_ID keeps the id documented in
+ * src/ray.h:22 (-1 = no hit). */
+enum { HGB_HIT_STEPS = 0, HGB_HIT_PRIM_ID = 1 };
+
+/* Device arrays that can be downloaded / uploaded. */
+enum {
+    HGB_ARRAY_ENTRIES     = 0,  /* Entry[num_entries]       4 B each  (grid.h:12)  */
+    HGB_ARRAY_CELLS       = 1,  /* Cell[num_cells]         32 B each  (grid.h:23)  */
+    HGB_ARRAY_SMALL_CELLS = 2,  /* SmallCell[num_cells]    16 B each  (grid.h:36)  */
+    HGB_ARRAY_REFS        = 3,  /* int[num_refs]                                     */
+    HGB_ARRAY_TRIS        = 4   /* Tri[num_tris]           48 B each  (prims.h:13) */
+};
+
+/* Identification. `hgb_impl()` returns "hagrid_b200" for this library and
+ * "reference" for the reference build of the same ABI. */
+HGB_API const char* hgb_impl(void);
+HGB_API const char* hgb_last_error(void);
+HGB_API int  hgb_device_count(void);
+/* Tuning/diagnostic switches of this library (no reference counterpart; the
+ * reference build of this ABI accepts and ignores them). Keys:
+ *   "traverse_variant"  0 = one thread per ray, 1 = persistent phase-scheduled (default)
+ * Returns 0 when the key is known. */
+HGB_API int  hgb_set_option(const char* key, int value);
+
+/* Scene life cycle: MemManager(keep) + Tri upload, main.cpp:471-478. */
+HGB_API hgb_scene* hgb_scene_create(int device, int keep_alive);
+HGB_API void       hgb_scene_destroy(hgb_scene* scene);
+/* `host_tris`: num_tris x 48 B {v0,nx,e1,ny,e2,nz} (prims.h:13-16). */
+HGB_API int  hgb_scene_set_tris(hgb_scene* scene, const void* host_tris, int num_tris);
+HGB_API int  hgb_scene_num_tris(const hgb_scene* scene);
+/* Peak bytes handed out by the scene's MemManager (mem_manager.h:104). */
+HGB_API size_t hgb_scene_peak_bytes(const hgb_scene* scene);
+
+/* The five construction stages (build.h:17,20,25,28,31).  hgb_build_grid
+ * first releases the previous grid arrays like main.cpp:496-498 does. */
+HGB_API int  hgb_build_grid(hgb_scene* scene, float top_density, float snd_density);
+HGB_API int  hgb_merge_grid(hgb_scene* scene, float alpha);
+HGB_API int  hgb_flatten_grid(hgb_scene* scene);
+HGB_API int  hgb_expand_grid(hgb_scene* scene, int iters);
+/* Returns 1 when compressed, 0 when refused (virtual dims >= 65536,
+ * compress.cu:41-44), negative on error. */
+HGB_API int  hgb_compress_grid(hgb_scene* scene);
+
+/* main.cpp:494-508: one event-timed (profile(), profile.cu:5-18) pass of
+ * build+merge+flatten+expand[+compress], `iters` times after `warmup`
+ * untimed passes; ms_out[iters] receives each pass' milliseconds. */
+HGB_API int  hgb_build_pipeline(hgb_scene* scene, float top_density, float snd_density,
+                        float alpha, int exp_iters, int compress,
+                        int warmup, int iters, float* ms_out);
+
+/* traverse.h:11 and :14.  Rays: 32 B {org,tmin,dir,tmax} (ray.h:9-20), hits:
+ * 16 B {id,t,u,v} (ray.h:23-33); `dev_*` are device pointers. The launch is
+ * asynchronous on the legacy default stream like the reference's. */
+HGB_API int  hgb_setup_traversal(hgb_scene* scene);
+HGB_API int  hgb_traverse_grid(hgb_scene* scene, const void* dev_rays, void* dev_hits,
+                       int num_rays, int hit_mode);
+/* main.cpp:414-425: `warmup` untimed launches then `iters` launches each
+ * timed with profile(); ms_out[iters]. */
+HGB_API int  hgb_traverse_timed(hgb_scene* scene, const void* dev_rays, void* dev_hits,
+                        int num_rays, int hit_mode, int warmup, int iters,
+                        float* ms_out);
+/* Interactive-frame shape (main.cpp:599-613): H2D rays, traverse, D2H hits,
+ * everything inside the call; host buffers may be pageable or pinned. */
+HGB_API int  hgb_traverse_grid_host(hgb_scene* scene, const void* host_rays,
+                            void* host_hits, int num_rays, int hit_mode);
+
+/* Grid inspection / transplant (parity tests move a grid between the
+ * reference build and this library through host memory). */
+HGB_API int  hgb_grid_get_info(const hgb_scene* scene, hgb_grid_info* info);
+HGB_API int  hgb_grid_download(const hgb_scene* scene, int which, void* host_dst, size_t bytes);
+/* `cells` is Cell[] or, when info->compressed, SmallCell[]. Arrays are taken
+ * from the scene's MemManager so the next build can free them. */
+HGB_API int  hgb_grid_upload(hgb_scene* scene, const hgb_grid_info* info,
+                     const void* host_entries, const void* host_cells,
+                     const void* host_refs);
+
+/* Raw device buffers from the scene's MemManager (mem_manager.h:46,75,84). */
+HGB_API void* hgb_device_alloc(hgb_scene* scene, size_t bytes);
+HGB_API void  hgb_device_free(hgb_scene* scene, void* dev_ptr);
+HGB_API int   hgb_copy_to_device(hgb_scene* scene, void* dev_dst, const void* host_src, size_t bytes);
+HGB_API int   hgb_copy_to_host(hgb_scene* scene, void* host_dst, const void* dev_src, size_t bytes);
+HGB_API int   hgb_device_synchronize(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* HAGRID_B200_H */

@@ -1,0 +1,59 @@
+#!/usr/bin/env bash
+# Builds the UNMODIFIED reference (cg-saarland/hagrid) for sm_100a from the
+# sources where they lie under /root/reference; outputs go only to oracle/_ref/
+# (git-ignored, but shipped to the GPU box by gpurun). Test oracle + reference
+# bench arm only: nothing in the product links or loads these files.
+#
+#   oracle/_ref/libhagrid_ref.so  include/hagrid_b200.h ABI over the reference
+#                                 (hagrid_b200/csrc/c_api.cpp, -DHGB_REFERENCE_BUILD)
+#   oracle/_ref/hagrid_ref        the reference's own main.cpp executable
+#
+# Semantics-neutral compile-compat edits applied to a scratch copy:
+#   parallel.cuh:13  private: -> public:   (nvcc host stubs name ResultType)
+#   build.cu:508     device lambda gets `-> int`, build.cu:727 gets `-> BBox`
+#   (CUB 2.8 cannot query return types of un-annotated extended lambdas)
+# The vendored CUB 1.8.0 does not compile with CUDA 12.9; the toolkit's CUB is used.
+# A second traverse object is built from a copy with `hit.id = steps;`
+# (traverse.cu:93) deleted and its two entry points renamed *_pid, so prim-id
+# parity can be checked against the reference's own arithmetic.
+set -euo pipefail
+REF=${HAGRID_REFERENCE:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+ROOT=$(dirname "$HERE")
+OUT=$HERE/_ref
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+[ -d "$REF/src" ] || { echo "reference sources not found at $REF (prebuilt oracle/_ref is used as is)"; exit 0; }
+mkdir -p "$OUT"
+W=$(mktemp -d)
+trap 'rm -rf "$W"' EXIT
+cp "$REF"/src/*.cu "$REF"/src/*.h "$REF"/src/*.cuh "$REF"/src/*.cpp "$W"/
+cd "$W"
+sed -i '13s/private:/public:/' parallel.cuh
+sed -i '508s/\[\] __device__ (int a, int b) {/[] __device__ (int a, int b) -> int {/' build.cu
+sed -i '727s/\[\] __device__ (BBox a, const BBox\& b) {/[] __device__ (BBox a, const BBox\& b) -> BBox {/' build.cu
+grep -q -- '-> int' build.cu && grep -q -- '-> BBox' build.cu && grep -q 'public:' parallel.cuh
+sed -e '/hit.id = steps;/d' -e 's/void setup_traversal(/void setup_traversal_pid(/' \
+    -e 's/void traverse_grid(/void traverse_grid_pid(/' traverse.cu > traverse_pid.cu
+! grep -q 'hit.id = steps' traverse_pid.cu
+
+NVFLAGS="-std=c++17 --expt-extended-lambda -lineinfo --use_fast_math -O3 -DNDEBUG -DHOST=__host__ -DDEVICE=__device__ \
+ -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wno-deprecated-declarations,-fvisibility=hidden -w"
+for f in build merge flatten expand compress mem_manager profile; do
+  $NVCC $NVFLAGS -c $f.cu -o $f.o &
+done
+$NVCC $NVFLAGS --maxrregcount=40 -c traverse.cu -o traverse.o &
+$NVCC $NVFLAGS --maxrregcount=40 -c traverse_pid.cu -o traverse_pid.o &
+wait
+CXXFLAGS="-O2 -DNDEBUG -DHOST= -DDEVICE= -fPIC -w -I/usr/local/cuda/include"
+g++ -std=c++11 $CXXFLAGS -I"$W" -I"$ROOT/include" -DHGB_REFERENCE_BUILD -fvisibility=hidden \
+    -c "$ROOT/hagrid_b200/csrc/c_api.cpp" -o c_api.o
+# c_api.o needs default visibility for the hagrid:: symbols it imports from the objects above
+g++ -shared -o "$OUT/libhagrid_ref.so" c_api.o build.o merge.o flatten.o expand.o compress.o mem_manager.o profile.o \
+    traverse.o traverse_pid.o -Wl,-Bsymbolic -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+g++ -std=c++11 $CXXFLAGS -I"$HERE/sdl_stub" -I"$W" -c main.cpp -o main.o
+g++ -std=c++11 $CXXFLAGS -I"$W" -c load_obj.cpp -o load_obj.o
+g++ -o "$OUT/hagrid_ref" main.o load_obj.o build.o merge.o flatten.o expand.o compress.o mem_manager.o profile.o traverse.o \
+    -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+# SASS of the reference traversal, for expression-shape comparison (not shipped in git)
+/usr/local/cuda/bin/cuobjdump -sass traverse_pid.o > "$OUT/traverse_pid.sass" 2>/dev/null || true
+echo "built: $(ls "$OUT")"
