@@ -14,7 +14,9 @@
 #   (CUB 2.8 cannot query return types of un-annotated extended lambdas)
 # The vendored CUB 1.8.0 does not compile with CUDA 12.9; the toolkit's CUB is used.
 # A second traverse object is built from a copy with `hit.id = steps;`
-# (traverse.cu:93) deleted and its two entry points renamed *_pid, so prim-id
+# (traverse.cu:93) deleted and its kernel + two entry points renamed *_pid
+# (template kernels have vague linkage: without the rename the linker would
+# fold both instantiations into one), so prim-id
 # parity can be checked against the reference's own arithmetic.
 set -euo pipefail
 REF=${HAGRID_REFERENCE:-/root/reference}
@@ -33,8 +35,11 @@ sed -i '508s/\[\] __device__ (int a, int b) {/[] __device__ (int a, int b) -> in
 sed -i '727s/\[\] __device__ (BBox a, const BBox\& b) {/[] __device__ (BBox a, const BBox\& b) -> BBox {/' build.cu
 grep -q -- '-> int' build.cu && grep -q -- '-> BBox' build.cu && grep -q 'public:' parallel.cuh
 sed -e '/hit.id = steps;/d' -e 's/void setup_traversal(/void setup_traversal_pid(/' \
-    -e 's/void traverse_grid(/void traverse_grid_pid(/' traverse.cu > traverse_pid.cu
-! grep -q 'hit.id = steps' traverse_pid.cu
+    -e 's/void traverse_grid(/void traverse_grid_pid(/' \
+    -e 's/__global__ void traverse(/__global__ void traverse_pid(/' -e 's/traverse<<</traverse_pid<<</g' \
+    traverse.cu > traverse_pid.cu
+if grep -q 'hit.id = steps' traverse_pid.cu; then echo "pid patch failed"; exit 1; fi
+[ "$(grep -c 'traverse_pid<<<' traverse_pid.cu)" = 2 ] || { echo "kernel rename failed"; exit 1; }
 
 NVFLAGS="-std=c++17 --expt-extended-lambda -lineinfo --use_fast_math -O3 -DNDEBUG -DHOST=__host__ -DDEVICE=__device__ \
  -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-Wno-deprecated-declarations,-fvisibility=hidden -w"
