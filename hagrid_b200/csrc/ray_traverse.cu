@@ -162,18 +162,91 @@ __device__ __forceinline__ void finish_ray(const RayState& r, Hit* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
-// Variant 0: one thread per ray (the reference's mapping), kept as the
-// in-library baseline that the scheduled kernel is measured against.
+// Ray packet layout. Camera rays arrive in raster order (src/main.cpp:52-66):
+// a warp of 32 consecutive rays is a 32x1 pixel strip whose rays fan out over
+// many cells. When the buffer is recognised as a W x H raster (detect_raster
+// below) thread -> ray assignment is re-tiled so that a warp traces an 8x4 pixel
+// tile: the lanes then walk (nearly) the same cells and test the same reference
+// lists, which is what the SIMT efficiency of this kernel depends on. The mapping
+// is a bijection on [0, num_rays) for any W, so it can only affect speed.
+// ---------------------------------------------------------------------------
+constexpr int kTileW = 8, kTileH = 4;
+
+__device__ __forceinline__ int tiled_ray_index(int thread, int width) {
+    const int tile = thread >> 5, lane = thread & 31;
+    const int tiles_per_row = width / kTileW;
+    const int ty = tile / tiles_per_row, tx = tile - ty * tiles_per_row;
+    return (ty * kTileH + (lane >> 3)) * width + tx * kTileW + (lane & 7);
+}
+
+/// One block. layout[0] <- W if rays[0..n) look like a W x (n / W) raster of a
+/// smoothly varying (org, dir) field with W % 8 == 0 and (n / W) % 4 == 0, else 0.
+/// The row length is the first index where the ray-to-ray delta breaks.
+__global__ void __launch_bounds__(256) detect_raster(const Ray* __restrict__ rays, int n, int* __restrict__ layout,
+                                                     volatile int* __restrict__ layout_host) {
+    __shared__ int row_break;
+    __shared__ int bad;
+    constexpr int kScan = 16384;
+    if (threadIdx.x == 0) { row_break = kScan; bad = 0; }
+    __syncthreads();
+    int width = 0;
+    if (n >= 4 * 64) {
+        const float4 a0 = dev::ldg4(reinterpret_cast<const float4*>(rays) + 0), b0 = dev::ldg4(reinterpret_cast<const float4*>(rays) + 1);
+        const float4 a1 = dev::ldg4(reinterpret_cast<const float4*>(rays) + 2), b1 = dev::ldg4(reinterpret_cast<const float4*>(rays) + 3);
+        const float step[6] = {a1.x - a0.x, a1.y - a0.y, a1.z - a0.z, b1.x - b0.x, b1.y - b0.y, b1.z - b0.z};
+        float tol = 0.0f;
+        for (int k = 0; k < 6; k++) tol = fmaxf(tol, fabsf(step[k]));
+        tol *= 0.25f;
+        const int limit = min(n, kScan);
+        auto continues = [&](int i) {
+            const float4 a = dev::ldg4(reinterpret_cast<const float4*>(rays + i)), b = dev::ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
+            const float4 pa = dev::ldg4(reinterpret_cast<const float4*>(rays + i - 1)), pb = dev::ldg4(reinterpret_cast<const float4*>(rays + i - 1) + 1);
+            const float d[6] = {a.x - pa.x, a.y - pa.y, a.z - pa.z, b.x - pb.x, b.y - pb.y, b.z - pb.z};
+            float err = 0.0f;
+            for (int k = 0; k < 6; k++) err = fmaxf(err, fabsf(d[k] - step[k]));
+            return err <= tol;                       // NaN compares false
+        };
+        if (tol > 0.0f) {
+            for (int i = 2 + threadIdx.x; i < limit; i += 256)
+                if (!continues(i)) { atomicMin(&row_break, i); break; }
+        }
+        __syncthreads();
+        width = row_break;
+        const bool shape_ok = tol > 0.0f && width < kScan && width >= 64 && width % kTileW == 0 && n % width == 0 &&
+                              (n / width) % kTileH == 0;
+        if (shape_ok) {
+            // the second and the last row must continue with the same step
+            for (int k = threadIdx.x; k < 62; k += 256) {
+                if (!continues(width + 1 + k)) atomicOr(&bad, 1);
+                if (!continues(n - width + 1 + k)) atomicOr(&bad, 1);
+            }
+        }
+        __syncthreads();
+        if (!shape_ok || bad) width = 0;
+    }
+    if (threadIdx.x == 0) {
+        layout[0] = width;
+        *layout_host = width;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Kernel A: one thread per ray, optionally re-tiled (coherent buffers).
 // ---------------------------------------------------------------------------
 template <typename CellT, bool kPrimId>
 __global__ void __launch_bounds__(128)
 traverse_per_thread(const __grid_constant__ TraversalParams P,
                     const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                     const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
-                    const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays) {
+                    const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
+                    const int* __restrict__ layout) {
     constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
-    const int id = threadIdx.x + blockDim.x * blockIdx.x;
+    int id = threadIdx.x + blockDim.x * blockIdx.x;
     if (id >= num_rays) return;
+    if (layout) {
+        const int width = __ldg(layout);
+        if (width > 0) id = tiled_ray_index(id, width);
+    }
     RayState r;
     if (start_ray(r, P, rays, id)) {
         while (true) {
@@ -205,7 +278,7 @@ traverse_per_thread(const __grid_constant__ TraversalParams P,
 }
 
 // ---------------------------------------------------------------------------
-// Variant 1: persistent warps, phase-scheduled (see the header comment).
+// Kernel B: persistent warps, phase-scheduled (incoherent buffers).
 // ---------------------------------------------------------------------------
 constexpr int kBlockThreads = 128;
 constexpr int kTriPhaseMinLanes = 12;   // leave the triangle phase when fewer lanes have work
@@ -288,22 +361,41 @@ traverse_persistent(const __grid_constant__ TraversalParams P,
     }
 }
 
-int* g_ray_counter[16] = {};
+/// Per-device launch state.
+struct DeviceState {
+    int* counter = nullptr;          // global ray counter of the persistent kernel
+    int* layout = nullptr;           // [0] = raster width found by detect_raster (0 = none)
+    int* layout_host = nullptr;      // pinned, mapped copy of layout[0]; -1 = detection still in flight
+    const void* seen_rays = nullptr; // buffer the layout belongs to
+    int seen_count = -1;
+    int num_sms = 0;
+};
 
-int* ray_counter() {
+DeviceState& device_state() {
+    static DeviceState states[64];
     int dev = 0;
     HGB_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) { std::fprintf(stderr, "hagrid_b200: device index out of range\n"); std::abort(); }
-    if (!g_ray_counter[dev]) HGB_CUDA(cudaMalloc(&g_ray_counter[dev], 64));
-    return g_ray_counter[dev];
+    if (dev < 0 || dev >= 64) { std::fprintf(stderr, "hagrid_b200: device index out of range\n"); std::abort(); }
+    DeviceState& st = states[dev];
+    if (!st.counter) {
+        HGB_CUDA(cudaMalloc(&st.counter, 128));
+        st.layout = st.counter + 16;
+        HGB_CUDA(cudaMemset(st.counter, 0, 128));
+        HGB_CUDA(cudaHostAlloc(&st.layout_host, sizeof(int), cudaHostAllocMapped));
+        *st.layout_host = 0;
+        HGB_CUDA(cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return st;
 }
 
+// 0: per thread, buffer order   1: persistent   2: per thread, re-tiled when a raster is detected
+// 3 (default): 2 for buffers that are (or may be) rasters, 1 once a buffer is known not to be one
 int g_variant = -1;
 
 int traverse_variant() {
     if (g_variant < 0) {
         const char* v = std::getenv("HGB_TRAVERSE_VARIANT");
-        g_variant = v ? std::atoi(v) : 1;
+        g_variant = v ? std::atoi(v) : 3;
     }
     return g_variant;
 }
@@ -316,24 +408,31 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
         std::abort();
     }
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
-    if (traverse_variant() == 0) {
-        traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128>>>(
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays);
-    } else {
-        static int blocks_per_sm = 0, num_sms = 0;
-        if (!num_sms) {
-            int dev = 0;
-            HGB_CUDA(cudaGetDevice(&dev));
-            HGB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DeviceState& st = device_state();
+    int variant = traverse_variant();
+    if (variant >= 2) {
+        if (rays != st.seen_rays || num_rays != st.seen_count) {
+            // new buffer: look at its layout on the device, asynchronously; this launch
+            // reads the answer from device memory, later launches also know it on the host
+            *static_cast<volatile int*>(st.layout_host) = -1;
+            int* host_alias = nullptr;
+            HGB_CUDA(cudaHostGetDevicePointer(&host_alias, st.layout_host, 0));
+            detect_raster<<<1, 256>>>(rays, num_rays, st.layout, host_alias);
+            st.seen_rays = rays;
+            st.seen_count = num_rays;
         }
+        if (variant == 3) variant = *static_cast<volatile int*>(st.layout_host) == 0 ? 1 : 2;
+    }
+    if (variant == 1) {
         int occ = 0;
         HGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traverse_persistent<CellT, kPrimId>, kBlockThreads, 0));
-        blocks_per_sm = occ > 0 ? occ : 1;
-        int* counter = ray_counter();
-        HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), 0));
-        const int blocks = min(num_sms * blocks_per_sm, round_div(num_rays, kBlockThreads));
+        HGB_CUDA(cudaMemsetAsync(st.counter, 0, sizeof(int), 0));
+        const int blocks = min(st.num_sms * max(occ, 1), round_div(num_rays, kBlockThreads));
         traverse_persistent<CellT, kPrimId><<<blocks, kBlockThreads>>>(
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, counter);
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, st.counter);
+    } else {
+        traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128>>>(
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, variant == 2 ? st.layout : nullptr);
     }
     HGB_CUDA(cudaGetLastError());
 }
