@@ -78,6 +78,7 @@ _SIGNATURES = {
     "hgb_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "hgb_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "hgb_device_synchronize": (C.c_int, []),
+    "hgb_kernel_launches": (C.c_ulonglong, []),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -113,6 +114,9 @@ class Library:
 
     def set_option(self, key: str, value: int):
         self.check(self.dll.hgb_set_option(key.encode(), int(value)), "set_option")
+
+    def kernel_launches(self) -> int:
+        return int(self.dll.hgb_kernel_launches())
 
     def synchronize(self):
         self.check(self.dll.hgb_device_synchronize(), "synchronize")

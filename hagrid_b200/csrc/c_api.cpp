@@ -32,6 +32,7 @@ void traverse_grid_pid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* 
 // Extra entry points of this library (hagrid_b200/include/hagrid/traverse.h).
 void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays);
 bool set_traversal_option(const char* key, int value);
+unsigned long long kernel_launch_count();
 #endif
 }
 
@@ -363,6 +364,14 @@ int hgb_copy_to_host(hgb_scene* s, void* host_dst, const void* dev_src, size_t b
     if (!bind(s)) return -1;
     if (bytes) s->mem.copy<Copy::DEV_TO_HST>(static_cast<char*>(host_dst), static_cast<const char*>(dev_src), bytes);
     return 0;
+}
+
+unsigned long long hgb_kernel_launches(void) {
+#ifdef HGB_REFERENCE_BUILD
+    return 0;
+#else
+    return kernel_launch_count();
+#endif
 }
 
 int hgb_device_synchronize(void) {

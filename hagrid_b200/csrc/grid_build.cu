@@ -438,7 +438,7 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
         unsigned lo = 0xFFFFFFFFu, hi = 0u;
         for (int k = 0; k < 3; k++) { init[k] = lo; init[3 + k] = hi; }
         HGB_CUDA(cudaMemcpyAsync(box_bits, init, sizeof(init), cudaMemcpyHostToDevice, 0));
-        scene_bounds<<<std::max(1, std::min(blocks_for(num_tris), 148 * 8)), kBlock>>>(tris, num_tris, box_bits);
+        scene_bounds<<<std::max(1, std::min(blocks_for(num_tris), 148 * 8)), kBlock>>>(tris, num_tris, box_bits); count_launch();
     }
     unsigned box_host[6];
     HGB_CUDA(cudaMemcpy(box_host, box_bits, sizeof(box_host), cudaMemcpyDeviceToHost));
@@ -469,8 +469,8 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
     int* scan_tmp = mem.alloc<int>(prim::num_tiles(num_tris) + 1);
     mem.zero(refs_per_cell, num_top);
     mem.zero(totals, 8);
-    count_refs<<<blocks_for(num_tris), kBlock>>>(P, tris, num_tris, counts, refs_per_cell);
-    top_cell_depths<<<blocks_for(num_top), kBlock>>>(P, refs_per_cell, snd_density, num_top, log_dims, totals + 1);
+    count_refs<<<blocks_for(num_tris), kBlock>>>(P, tris, num_tris, counts, refs_per_cell); count_launch();
+    top_cell_depths<<<blocks_for(num_top), kBlock>>>(P, refs_per_cell, snd_density, num_top, log_dims, totals + 1); count_launch();
     prim::exclusive_scan<int>(prim::LoadInt{counts}, num_tris, start_emit, scan_tmp, totals + 0);
     int host_totals[4];
     HGB_CUDA(cudaMemcpy(host_totals, totals, 2 * sizeof(int), cudaMemcpyDeviceToHost));
@@ -492,8 +492,8 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
     int* split = mem.alloc<int>(num_top);
     int num_cells = num_top;
     mem.zero(split, num_top);
-    emit_top_cells<<<blocks_for(num_top), kBlock>>>(P, cells, num_top);
-    emit_filter_refs<<<blocks_for(num_tris), kBlock>>>(P, tris, num_tris, start_emit, log_dims, ref_ids, cell_ids, split);
+    emit_top_cells<<<blocks_for(num_top), kBlock>>>(P, cells, num_top); count_launch();
+    emit_filter_refs<<<blocks_for(num_tris), kBlock>>>(P, tris, num_tris, start_emit, log_dims, ref_ids, cell_ids, split); count_launch();
     mem.free(start_emit);
 
     // ---- octree refinement, one level per iteration (build_iter, src/build.cu:528-619)
@@ -511,7 +511,7 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
 
         prim::exclusive_scan<int>(SplitToEight{split}, num_cells, child_start, reinterpret_cast<int*>(scan_tmp64), totals + 2);
         if (num_refs > 0)
-            classify_refs<<<blocks_for(num_refs), kBlock>>>(P, tris, ref_ids, cell_ids, cells, split, num_refs, codes);
+            classify_refs<<<blocks_for(num_refs), kBlock>>>(P, tris, ref_ids, cell_ids, cells, split, num_refs, codes); count_launch();
         prim::exclusive_scan<unsigned long long>(CodeCounts{codes}, num_refs, pos, scan_tmp64, totals64);
 
         struct { int pad[2]; int num_children_cells; int pad2; unsigned long long ref_totals; } host;
@@ -538,8 +538,8 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
         if (num_refs > 0)
             distribute_refs<<<blocks_for(num_refs), kBlock>>>(P, ref_ids, cell_ids, codes, pos, child_start, cells, log_dims, level,
                                                               num_refs, num_new_refs, L.kept_refs, L.kept_cells,
-                                                              next_refs, next_cell_ids, next_split);
-        emit_children<<<blocks_for(num_cells), kBlock>>>(cells, split, child_start, num_cells, L.entries, next_cells);
+                                                              next_refs, next_cell_ids, next_split); count_launch();
+        emit_children<<<blocks_for(num_cells), kBlock>>>(cells, split, child_start, num_cells, L.entries, next_cells); count_launch();
         HGB_CUDA(cudaGetLastError());
 
         mem.free(child_start);
@@ -582,10 +582,10 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
     int* out_keys = mem.alloc<int>(std::max(total_refs, 1));
     for (int i = 0, cell_off = 0, ref_off = 0; i < num_levels; i++) {
         const Level& L = levels[i];
-        finish_level<<<blocks_for(L.num_cells), kBlock>>>(L.cells, leaf_index, entries, out_cells, cell_off, cell_off + L.num_cells, L.num_cells);
+        finish_level<<<blocks_for(L.num_cells), kBlock>>>(L.cells, leaf_index, entries, out_cells, cell_off, cell_off + L.num_cells, L.num_cells); count_launch();
         if (L.num_kept > 0)
             gather_refs<<<blocks_for(L.num_kept), kBlock>>>(L.kept_refs, L.kept_cells, leaf_index, cell_off, L.num_kept,
-                                                            out_refs + ref_off, out_keys + ref_off);
+                                                            out_refs + ref_off, out_keys + ref_off); count_launch();
         cell_off += L.num_cells;
         ref_off += L.num_kept;
     }
@@ -600,7 +600,7 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
         int* sort_tmp = mem.alloc<int>(prim::sort_scratch_ints(total_refs));
         const bool in_alt = prim::sort_pairs(out_keys, out_refs, alt_keys, alt_refs, total_refs, ilog2(num_leaves), sort_tmp);
         if (in_alt) { std::swap(out_refs, alt_refs); std::swap(out_keys, alt_keys); }
-        cell_ranges<<<blocks_for(total_refs), kBlock>>>(out_keys, out_cells, total_refs);
+        cell_ranges<<<blocks_for(total_refs), kBlock>>>(out_keys, out_cells, total_refs); count_launch();
         HGB_CUDA(cudaGetLastError());
         mem.free(alt_refs);
         mem.free(alt_keys);

@@ -74,7 +74,7 @@ bool compress_grid(MemManager& mem, Grid& grid) {
     HGB_CUDA(cudaMemcpy(&num_words, total_dev, sizeof(int), cudaMemcpyDeviceToHost));
     int* out_refs = mem.alloc<int>(std::max(num_words, 1));
     if (num_cells > 0)
-        emit_small_cells<<<(num_cells + kBlock - 1) / kBlock, kBlock>>>(grid.cells, grid.ref_ids, list_start, small_cells, out_refs, num_cells);
+        emit_small_cells<<<(num_cells + kBlock - 1) / kBlock, kBlock>>>(grid.cells, grid.ref_ids, list_start, small_cells, out_refs, num_cells); count_launch();
     HGB_CUDA(cudaGetLastError());
 
     grid.small_cells = small_cells;

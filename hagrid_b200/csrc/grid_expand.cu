@@ -132,11 +132,11 @@ void expand_grid(MemManager& mem, Grid& grid, const Tri*, int iters) {
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
     const int blocks = (grid.num_cells + kBlock - 1) / kBlock;
     for (int i = 0; i < iters && grid.num_cells > 0; i++) {
-        grow_cells<0><<<blocks, kBlock>>>(P, entries, grid.ref_ids, grid.cells, other, flags, grid.num_cells);
+        grow_cells<0><<<blocks, kBlock>>>(P, entries, grid.ref_ids, grid.cells, other, flags, grid.num_cells); count_launch();
         std::swap(other, grid.cells);
-        grow_cells<1><<<blocks, kBlock>>>(P, entries, grid.ref_ids, grid.cells, other, flags, grid.num_cells);
+        grow_cells<1><<<blocks, kBlock>>>(P, entries, grid.ref_ids, grid.cells, other, flags, grid.num_cells); count_launch();
         std::swap(other, grid.cells);
-        grow_cells<2><<<blocks, kBlock>>>(P, entries, grid.ref_ids, grid.cells, other, flags, grid.num_cells);
+        grow_cells<2><<<blocks, kBlock>>>(P, entries, grid.ref_ids, grid.cells, other, flags, grid.num_cells); count_launch();
         std::swap(other, grid.cells);
     }
     HGB_CUDA(cudaGetLastError());

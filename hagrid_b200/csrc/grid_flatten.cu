@@ -116,7 +116,7 @@ void flatten_grid(MemManager& mem, Grid& grid) {
     for (int level = grid.shift; level >= 0; level--) {
         const int first = level > 0 ? grid.offsets[level - 1] : 0;
         const int count = grid.offsets[level] - first;
-        if (count > 0) collapse_and_depth<<<blocks_for(count), kBlock>>>(entries, depths, first, count);
+        if (count > 0) collapse_and_depth<<<blocks_for(count), kBlock>>>(entries, depths, first, count); count_launch();
     }
 
     // where each flattened node starts inside its group, and the size of every group
@@ -137,13 +137,13 @@ void flatten_grid(MemManager& mem, Grid& grid) {
 
     uint32_t* out = mem.alloc<uint32_t>(total_entries);
     std::vector<int> new_offsets;
-    copy_top<<<blocks_for(grid.offsets[0]), kBlock>>>(entries, node_start, depths, out, grid.offsets[0]);
+    copy_top<<<blocks_for(grid.offsets[0]), kBlock>>>(entries, node_start, depths, out, grid.offsets[0]); count_launch();
     for (int level = 0; level < grid.shift; level += kFlatLevels) {
         const int first = level > 0 ? grid.offsets[level - 1] : 0;
         const int count = grid.offsets[level] - first;
         const int next_offset = level + kFlatLevels < grid.shift ? group_offset[level + kFlatLevels] : 0;
         if (count > 0)
-            write_nodes<<<blocks_for(count), kBlock>>>(entries, node_start, depths, out, first, group_offset[level], next_offset, count);
+            write_nodes<<<blocks_for(count), kBlock>>>(entries, node_start, depths, out, first, group_offset[level], next_offset, count); count_launch();
         new_offsets.push_back(group_offset[level]);
     }
     new_offsets.push_back(total_entries);

@@ -246,14 +246,14 @@ void merge_pass(const MergeParams& P, Grid& grid, Cell*& spare_cells, int*& spar
     const int num_cells = grid.num_cells;
     auto entries = reinterpret_cast<uint32_t*>(grid.entries);
     HGB_CUDA(cudaMemsetAsync(b.prevs, 0xFF, sizeof(int) * num_cells, 0));
-    pair_up<axis><<<blocks_for(num_cells), kBlock>>>(P, entries, grid.cells, grid.ref_ids, b.merge_counts, b.nexts, b.prevs, empty_mask, num_cells);
-    resolve_chains<<<blocks_for(num_cells), kBlock>>>(b.nexts, b.prevs, b.merge_counts, b.kept, b.new_counts, num_cells);
+    pair_up<axis><<<blocks_for(num_cells), kBlock>>>(P, entries, grid.cells, grid.ref_ids, b.merge_counts, b.nexts, b.prevs, empty_mask, num_cells); count_launch();
+    resolve_chains<<<blocks_for(num_cells), kBlock>>>(b.nexts, b.prevs, b.merge_counts, b.kept, b.new_counts, num_cells); count_launch();
     prim::exclusive_scan<unsigned long long>(KeptAndCount{b.kept, b.new_counts}, num_cells, b.scan, b.scan_tmp, b.totals);
     unsigned long long totals = 0;
     HGB_CUDA(cudaMemcpy(&totals, b.totals, sizeof(totals), cudaMemcpyDeviceToHost));
     merge_cells<axis><<<blocks_for(num_cells), kBlock>>>(P, entries, grid.cells, grid.ref_ids, b.scan, b.merge_counts, b.new_cell_ids,
-                                                         spare_cells, spare_refs, num_cells);
-    remap_entries<<<blocks_for(grid.num_entries), kBlock>>>(entries, b.new_cell_ids, grid.num_entries);
+                                                         spare_cells, spare_refs, num_cells); count_launch();
+    remap_entries<<<blocks_for(grid.num_entries), kBlock>>>(entries, b.new_cell_ids, grid.num_entries); count_launch();
     HGB_CUDA(cudaGetLastError());
     std::swap(spare_cells, grid.cells);
     std::swap(spare_refs, grid.ref_ids);

@@ -137,9 +137,9 @@ void exclusive_scan(F f, int n, T* out, T* tile_scratch, T* total_out) {
         return;
     }
     const int tiles = num_tiles(n);
-    scan_reduce_tiles<T, F><<<tiles, kThreads>>>(f, n, tile_scratch);
-    scan_tile_sums<T><<<1, kThreads>>>(tile_scratch, tiles, total_out);
-    scan_apply_tiles<T, F><<<tiles, kThreads>>>(f, n, tile_scratch, out);
+    scan_reduce_tiles<T, F><<<tiles, kThreads>>>(f, n, tile_scratch); count_launch();
+    scan_tile_sums<T><<<1, kThreads>>>(tile_scratch, tiles, total_out); count_launch();
+    scan_apply_tiles<T, F><<<tiles, kThreads>>>(f, n, tile_scratch, out); count_launch();
     HGB_CUDA(cudaGetLastError());
 }
 
@@ -245,9 +245,9 @@ inline bool sort_pairs(int* keys, int* vals, int* keys_alt, int* vals_alt, int n
     for (int shift = 0; shift < bits; shift += kRadixBits) {
         int* kin = in_alt ? keys_alt : keys;   int* vin = in_alt ? vals_alt : vals;
         int* kout = in_alt ? keys : keys_alt;  int* vout = in_alt ? vals : vals_alt;
-        radix_histogram<<<tiles, kThreads>>>(kin, n, shift, tiles, hist);
+        radix_histogram<<<tiles, kThreads>>>(kin, n, shift, tiles, hist); count_launch();
         exclusive_scan<int>(LoadInt{hist}, hist_n, hist, scan_tiles, (int*)nullptr);
-        radix_scatter<<<tiles, kThreads>>>(kin, vin, kout, vout, n, shift, tiles, hist);
+        radix_scatter<<<tiles, kThreads>>>(kin, vin, kout, vout, n, shift, tiles, hist); count_launch();
         in_alt = !in_alt;
     }
     HGB_CUDA(cudaGetLastError());

@@ -417,7 +417,7 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
             *static_cast<volatile int*>(st.layout_host) = -1;
             int* host_alias = nullptr;
             HGB_CUDA(cudaHostGetDevicePointer(&host_alias, st.layout_host, 0));
-            detect_raster<<<1, 256>>>(rays, num_rays, st.layout, host_alias);
+            detect_raster<<<1, 256>>>(rays, num_rays, st.layout, host_alias); count_launch();
             st.seen_rays = rays;
             st.seen_count = num_rays;
         }
@@ -429,10 +429,10 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
         HGB_CUDA(cudaMemsetAsync(st.counter, 0, sizeof(int), 0));
         const int blocks = min(st.num_sms * max(occ, 1), round_div(num_rays, kBlockThreads));
         traverse_persistent<CellT, kPrimId><<<blocks, kBlockThreads>>>(
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, st.counter);
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, st.counter); count_launch();
     } else {
         traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128>>>(
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, variant == 2 ? st.layout : nullptr);
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, variant == 2 ? st.layout : nullptr); count_launch();
     }
     HGB_CUDA(cudaGetLastError());
 }

@@ -9,6 +9,9 @@
 
 namespace hagrid {
 
+unsigned long long g_kernel_launches = 0;
+unsigned long long kernel_launch_count() { return g_kernel_launches; }
+
 namespace {
 
 /// Stream-ordered allocation on the legacy default stream: the pool keeps

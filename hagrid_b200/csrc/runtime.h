@@ -15,6 +15,11 @@ inline void check_cuda(cudaError_t err, const char* what, const char* file, int 
     }
 }
 
+/// Number of kernels this library has launched since it was loaded (bench.py reports
+/// the count inside its timed region as `gpu_launches`).
+extern unsigned long long g_kernel_launches;
+inline void count_launch(int n = 1) { g_kernel_launches += (unsigned long long)n; }
+
 } // namespace hagrid
 
 #define HGB_CUDA(call) ::hagrid::check_cuda((call), #call, __FILE__, __LINE__)

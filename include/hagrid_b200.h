@@ -139,6 +139,9 @@ HGB_API void  hgb_device_free(hgb_scene* scene, void* dev_ptr);
 HGB_API int   hgb_copy_to_device(hgb_scene* scene, void* dev_dst, const void* host_src, size_t bytes);
 HGB_API int   hgb_copy_to_host(hgb_scene* scene, void* host_dst, const void* dev_src, size_t bytes);
 HGB_API int   hgb_device_synchronize(void);
+/* Kernels launched by this library since load (0 for the reference build, which
+ * does not count). bench.py reports the difference over its timed region. */
+HGB_API unsigned long long hgb_kernel_launches(void);
 
 #ifdef __cplusplus
 }

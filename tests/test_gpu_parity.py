@@ -1,0 +1,315 @@
+"""GPU tier (run with -m gpu on the B200 box): the CUDA path, called through the C ABI,
+against (1) the golden fixtures produced by the reference, (2) the CPU oracle on seeded
+inputs, (3) the reference rebuilt for sm_100a when oracle/_ref is present, and (4)
+size-independent properties at BASELINE.json's full sizes. Integer/index results are
+compared bit-exactly; hit distances bit-exactly against the reference and within 1e-5
+(north_star tolerance) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from hagrid_b200 import HIT_PRIM_ID, HIT_STEPS, RAY_DTYPE, Scene, scenes
+from hagrid_b200.api import GridInfo
+from util import FIXTURES, STAGES, Golden, grid_diff, t_close
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = (0, 1, 2, 3)    # per-thread / persistent / per-thread re-tiled / automatic
+
+
+def run_stage(sc, stage, g):
+    if stage == "build": sc.build_grid(g.top_density, g.snd_density)
+    elif stage == "merge": sc.merge_grid(g.alpha)
+    elif stage == "flatten": sc.flatten_grid()
+    elif stage == "expand": sc.expand_grid(g.expansion)
+    elif stage == "compress": assert sc.compress_grid()
+
+
+def info_from_dict(d):
+    gi = GridInfo()
+    gi.bbox_min[:] = d["bbox_min"]; gi.bbox_max[:] = d["bbox_max"]; gi.dims[:] = d["dims"]
+    gi.shift, gi.num_cells, gi.num_entries, gi.num_refs = d["shift"], d["num_cells"], d["num_entries"], d["num_refs"]
+    gi.compressed = d["compressed"]; gi.num_offsets = len(d["offsets"])
+    gi.offsets[:len(d["offsets"])] = d["offsets"]
+    return gi
+
+
+def upload(sc, stage_tuple):
+    info, e, c, r = stage_tuple
+    sc.upload(info_from_dict(info), e, c, r)
+
+
+def dump(sc):
+    gi, e, c, r = sc.download()
+    return gi.as_dict(), (e, c, r)
+
+
+@pytest.fixture(scope="module", params=FIXTURES)
+def golden(request):
+    return Golden(request.param)
+
+
+def test_native_library_is_loaded(lib):
+    assert lib.impl == "hagrid_b200" and lib.path.name == "libhagrid_b200.so"
+
+
+def test_pipeline_matches_reference_golden(lib, golden):
+    sc = Scene(golden.tris, lib=lib)
+    for stage in STAGES:
+        run_stage(sc, stage, golden)
+        info, arrays = dump(sc)
+        assert grid_diff(info, arrays, golden.stage[stage]) == [], stage
+    sc.close()
+
+
+@pytest.mark.parametrize("stage", STAGES[1:])
+def test_each_stage_on_reference_input(lib, golden, stage):
+    sc = Scene(golden.tris, lib=lib)
+    upload(sc, golden.stage[STAGES[STAGES.index(stage) - 1]])
+    run_stage(sc, stage, golden)
+    info, arrays = dump(sc)
+    assert grid_diff(info, arrays, golden.stage[stage]) == []
+    sc.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("cells", ["cell", "small"])
+def test_traversal_bit_exact_on_reference_grid(lib, golden, cells, variant):
+    sc = Scene(golden.tris, lib=lib)
+    upload(sc, golden.stage["expand" if cells == "cell" else "compress"])
+    sc.setup_traversal()
+    lib.set_option("traverse_variant", variant)
+    try:
+        for mode, key in ((HIT_STEPS, "steps"), (HIT_PRIM_ID, "ids")):
+            got, want = sc.trace(golden.rays, mode), golden.hits[f"hits_{cells}_{key}"]
+            assert np.array_equal(got["id"], want["id"])
+            assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+            assert (got["u"] == 0).all() and (got["v"] == 0).all()
+    finally:
+        lib.set_option("traverse_variant", 3)
+        sc.close()
+
+
+def test_pipeline_against_cpu_oracle(lib):
+    """Seeded input outside the fixtures: GPU construction vs the CPU restatement, then the
+    oracle traces the GPU-built grid."""
+    from oracle import oracle
+    tris = scenes.small_mixed(2500, seed=21)
+    sc = Scene(tris, lib=lib)
+    cpu = oracle.Grid.build(tris, 0.12, 2.4)
+    sc.build_grid(0.12, 2.4)
+    for stage in ("merge", "flatten", "expand"):
+        getattr(cpu, stage)()
+        getattr(sc, stage + "_grid")()
+    info, arrays = dump(sc)
+    assert grid_diff(info, arrays, (cpu.info(),) + cpu.arrays()) == []
+    sc.setup_traversal()
+    rays = scenes.random_rays(tris, 20000, seed=4, tmax=10.0)
+    gpu_ids, gpu_steps = sc.trace(rays, HIT_PRIM_ID), sc.trace(rays, HIT_STEPS)
+    cpu_ids, cpu_steps = cpu.traverse(tris, rays, 1, threads=4), cpu.traverse(tris, rays, 0, threads=4)
+    assert (gpu_ids["id"] == cpu_ids["id"]).mean() >= 0.999          # near-ties may flip without MUFU.RCP
+    assert (gpu_steps["id"] == cpu_steps["id"]).mean() >= 0.999
+    same = gpu_ids["id"] == cpu_ids["id"]
+    assert t_close(gpu_ids["t"][same], cpu_ids["t"][same]).all()
+    sc.close()
+
+
+def test_against_reference_build(lib, ref_lib):
+    """Differential test against cg-saarland/hagrid itself (rebuilt for sm_100a) on a fresh seeded
+    scene: every construction stage byte-identical, all hits bit-identical, raster and random rays."""
+    tris = scenes.small_mixed(20000, seed=33)
+    a, b = Scene(tris, lib=ref_lib), Scene(tris, lib=lib)
+    a.build_grid(0.15, 3.0); b.build_grid(0.15, 3.0)
+    for stage in ("merge", "flatten", "expand"):
+        getattr(a, stage + "_grid")(); getattr(b, stage + "_grid")()
+        ia, aa = dump(a); ib, ab = dump(b)
+        assert grid_diff(ib, ab, (ia,) + aa) == [], stage
+    lo, hi = scenes.scene_bbox(tris)
+    raster = scenes.primary_rays(lo - (hi - lo) * 0.6, 0.5 * (lo + hi), (0, 1, 0), 50.0, 256, 128, 50.0)
+    rays = np.concatenate([raster, scenes.random_rays(tris, 200000, seed=8)])
+    for compressed in (False, True):
+        if compressed:
+            assert a.compress_grid() and b.compress_grid()
+        a.setup_traversal(); b.setup_traversal()
+        for buf in (raster, rays):
+            for mode in (HIT_STEPS, HIT_PRIM_ID):
+                want, got = a.trace(buf, mode), b.trace(buf, mode)
+                assert np.array_equal(got["id"], want["id"])
+                assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    a.close(); b.close()
+
+
+# ----------------------------------------------------------------------------- full-size properties
+@pytest.fixture(scope="module")
+def sponza(lib):
+    tris = scenes.sponza262k()
+    sc = Scene(tris, lib=lib)
+    ms = sc.build_all(0.15, 3.0, 0.995, 3, compress=False, warmup=0, iters=1)
+    sc.setup_traversal()
+    yield tris, sc, float(ms[0])
+    sc.close()
+
+
+def test_c2_grid_invariants(sponza):
+    tris, sc, _ = sponza
+    gi, entries, cells, refs = sc.download()
+    vd = np.array(gi.dims[:]) << gi.shift
+    assert (cells["min"] >= 0).all() and (cells["max"] <= vd).all() and (cells["min"] < cells["max"]).all()
+    assert int((cells["end"] - cells["begin"]).sum()) == gi.num_refs          # ranges tile the reference array
+    assert refs.min() >= 0 and refs.max() < tris.shape[0]
+    leaf = (entries & 3) == 0
+    assert np.array_equal(np.unique(entries[leaf] >> 2), np.arange(gi.num_cells))   # every cell owns a voxel
+    assert ((entries[~leaf] >> 2) < gi.num_entries).all()
+    assert np.unique(refs).shape[0] == np.unique(refs[refs >= 0]).shape[0]
+
+
+def test_c2_primary_rays_all_variants_agree_and_closest_hit_properties(lib, sponza):
+    tris, sc, _ = sponza
+    rays = scenes.default_view(tris)              # 1920 x 1080, the BASELINE.json C2 ray buffer
+    try:
+        results = {}
+        for v in VARIANTS:
+            lib.set_option("traverse_variant", v)
+            results[v] = sc.trace(rays, HIT_PRIM_ID)
+        base = results[0]
+        for v in VARIANTS[1:]:
+            assert np.array_equal(results[v]["id"], base["id"])
+            assert np.array_equal(results[v]["t"].view(np.uint32), base["t"].view(np.uint32))
+        lib.set_option("traverse_variant", 3)
+        assert np.array_equal(sc.trace(rays, HIT_PRIM_ID)["id"], base["id"])          # idempotent
+        hit = base["id"] >= 0
+        assert hit.mean() > 0.9                                                       # camera is inside the atrium
+        # nothing is closer than the reported hit: stopping just short of it must find nothing
+        short = rays.copy()
+        short["tmax"][hit] = base["t"][hit] * np.float32(0.999)
+        res = sc.trace(short, HIT_PRIM_ID)
+        assert (res["id"][hit] == -1).all() and np.array_equal(res["t"][hit], short["tmax"][hit])
+        # and looking further must not change it
+        far = rays.copy()
+        far["tmax"] = rays["tmax"] * np.float32(4.0)
+        res = sc.trace(far, HIT_PRIM_ID)
+        assert np.array_equal(res["id"][hit], base["id"][hit]) and np.array_equal(res["t"][hit], base["t"][hit])
+        # the hit point lies on the reported triangle's plane (relative to scene size)
+        tr = tris[base["id"][hit]]
+        p = rays["org"][hit].astype(np.float64) + rays["dir"][hit].astype(np.float64) * base["t"][hit][:, None].astype(np.float64)
+        n = np.stack([tr["nx"], tr["ny"], tr["nz"]], 1).astype(np.float64)
+        n /= np.linalg.norm(n, axis=1, keepdims=True)
+        assert np.abs(((p - tr["v0"]) * n).sum(1)).max() < 1e-3
+    finally:
+        lib.set_option("traverse_variant", 3)
+
+
+def test_c3_compressed_grid_gives_same_hits(lib, sponza):
+    tris, sc, _ = sponza
+    rays = scenes.random_rays(tris, 1 << 20)
+    want = sc.trace(rays, HIT_PRIM_ID)
+    want_steps = sc.trace(rays, HIT_STEPS)
+    sc2 = Scene(tris, lib=lib)
+    sc2.build_all(0.15, 3.0, 0.995, 3, compress=True)
+    assert sc2.info().compressed == 1
+    sc2.setup_traversal()
+    got = sc2.trace(rays, HIT_PRIM_ID)
+    got_steps = sc2.trace(rays, HIT_STEPS)
+    sc.setup_traversal()
+    assert np.array_equal(got["id"], want["id"]) and np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    assert (got_steps["id"] >= want_steps["id"]).all()       # + one sentinel read per non-empty cell
+    sc2.close()
+
+
+def test_build_is_deterministic(lib):
+    tris = scenes.hairball(60000, seed=2)
+    a, b = Scene(tris, lib=lib), Scene(tris, keep_alive=True, lib=lib)
+    a.build_all(0.12, 2.4); b.build_all(0.12, 2.4, warmup=1, iters=2)
+    ia, aa = dump(a); ib, ab = dump(b)
+    assert grid_diff(ib, ab, (ia,) + aa) == []
+    assert a.peak_bytes() > 0
+    a.close(); b.close()
+
+
+# ----------------------------------------------------------------------------- edge cases
+def test_ragged_and_empty_ray_buffers(lib):
+    g = Golden("cornell32")
+    sc = Scene(g.tris, lib=lib)
+    sc.build_all(g.top_density, g.snd_density)
+    sc.setup_traversal()
+    full = sc.trace(g.rays, HIT_PRIM_ID)
+    try:
+        for v in VARIANTS:
+            lib.set_option("traverse_variant", v)
+            for n in (1, 31, 33, 127, 129, 1000):
+                part = sc.trace(g.rays[:n], HIT_PRIM_ID)
+                assert np.array_equal(part["id"], full["id"][:n]) and np.array_equal(part["t"], full["t"][:n])
+            sc.traverse(0, 0, 0, HIT_PRIM_ID)        # zero rays: a no-op, not an error
+    finally:
+        lib.set_option("traverse_variant", 3)
+    sc.close()
+
+
+def test_rays_missing_the_grid_and_degenerate_rays(lib):
+    g = Golden("cornell32")
+    sc = Scene(g.tris, lib=lib)
+    sc.build_all(g.top_density, g.snd_density)
+    sc.setup_traversal()
+    rays = np.zeros(64, dtype=RAY_DTYPE)
+    rays["org"] = (5000.0, 5000.0, 5000.0); rays["dir"] = (1.0, 0.5, 0.25); rays["tmax"] = 123.0
+    rays["dir"][32:] = 0.0
+    for mode in (HIT_PRIM_ID, HIT_STEPS):
+        res = sc.trace(rays, mode)
+        assert (res["t"] == 123.0).all()
+        assert (res["id"] == (-1 if mode == HIT_PRIM_ID else 0)).all()
+    sc.close()
+
+
+def test_single_and_degenerate_triangles(lib):
+    tris = scenes.make_tris([[0, 0, 0], [0, 0, 0]], [[1, 0, 0], [0, 0, 0]], [[0, 1, 0], [0, 0, 0]])   # second one is a point
+    for t in (tris[:1], tris):
+        sc = Scene(t, lib=lib)
+        sc.build_all(0.12, 2.4)
+        sc.setup_traversal()
+        rays = np.zeros(2, dtype=RAY_DTYPE)
+        rays["org"] = [(0.25, 0.25, 1.0), (2.0, 2.0, 1.0)]; rays["dir"] = (0, 0, -1); rays["tmax"] = 10.0
+        res = sc.trace(rays, HIT_PRIM_ID)
+        assert res["id"][0] == 0 and abs(res["t"][0] - 1.0) < 1e-6 and res["id"][1] == -1
+        sc.close()
+
+
+def test_optional_stages_can_be_skipped(lib):
+    """alpha <= 0 disables merging (src/merge.cu:357), iters == 0 disables expansion (src/expand.cu:201)."""
+    g = Golden("soup800")
+    sc = Scene(g.tris, lib=lib)
+    sc.build_grid(g.top_density, g.snd_density)
+    before = dump(sc)
+    sc.merge_grid(0.0)
+    after = dump(sc)
+    assert grid_diff(after[0], after[1], (before[0],) + before[1]) == []
+    sc.flatten_grid()
+    before = dump(sc)
+    sc.expand_grid(0)
+    after = dump(sc)
+    assert grid_diff(after[0], after[1], (before[0],) + before[1]) == []
+    sc.setup_traversal()
+    want = Golden("soup800").hits["hits_cell_ids"]
+    got = sc.trace(g.rays, HIT_PRIM_ID)      # an unmerged, unexpanded grid still finds the same closest hits
+    assert np.array_equal(got["id"], want["id"])
+    sc.close()
+
+
+def test_host_buffer_entry_point(lib):
+    g = Golden("soup800")
+    sc = Scene(g.tris, lib=lib)
+    upload(sc, g.stage["expand"])
+    sc.setup_traversal()
+    got = sc.traverse_host(g.rays, HIT_PRIM_ID)
+    assert np.array_equal(got["id"], g.hits["hits_cell_ids"]["id"])
+    assert np.array_equal(got["t"].view(np.uint32), g.hits["hits_cell_ids"]["t"].view(np.uint32))
+    sc.close()
+
+
+def test_buffer_pool_reuse(lib):
+    sc = Scene(scenes.cornell32(), keep_alive=True, lib=lib)
+    a = sc.device_alloc(1 << 20)
+    sc.device_free(a)
+    b = sc.device_alloc(1 << 20)
+    assert a == b                                # keep mode hands the retained slot back
+    sc.device_free(b)
+    assert sc.peak_bytes() >= 1 << 20
+    sc.close()

@@ -32,6 +32,7 @@ sm.upload(gi, e, c, r)
 sm.setup_traversal()
 n = rays.shape[0]
 out = {}
+ref_hits = None
 for label, sc, lib_, vs in (("ref", sr, ref, [0] if with_ref else []), ("mine", sm, mine, variants)):
     if not vs:
         continue
@@ -40,6 +41,9 @@ for label, sc, lib_, vs in (("ref", sr, ref, [0] if with_ref else []), ("mine", 
     for v in vs:
         lib_.set_option("traverse_variant", v)
         ms = sc.traverse_timed(d_rays, d_hits, n, HIT_PRIM_ID, warmup=min(3, iters), iters=iters)
-        out[f"{label}_v{v}"] = {"ms_median": float(np.median(ms)), "ms_min": float(ms.min()),
-                                "mrays_s": float(n * len(ms) / (1000.0 * ms.sum()))}
+        hits = sc.to_host(np.empty(n, dtype=np.dtype([("id", "<i4"), ("t", "<u4"), ("u", "<f4"), ("v", "<f4")])), d_hits)
+        if label == "ref": ref_hits = hits
+        same = None if ref_hits is None else int(((hits["id"] == ref_hits["id"]) & (hits["t"] == ref_hits["t"])).sum())
+        out[f"{label}_v{v}"] = {"ms_median": round(float(np.median(ms)), 4), "ms_min": round(float(ms.min()), 4),
+                                "mrays_s": round(float(n * len(ms) / (1000.0 * ms.sum())), 1), "identical_hits": same, "n": n}
 print(json.dumps(out))
