@@ -445,6 +445,20 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
     BBox grid_bb(vec3(from_ordered(box_host[0]), from_ordered(box_host[1]), from_ordered(box_host[2])),
                  vec3(from_ordered(box_host[3]), from_ordered(box_host[4]), from_ordered(box_host[5])));
 
+    // Domain extension (the only place this build leaves the reference's arithmetic): a scene box
+    // with a zero extent (all triangles in one axis-aligned plane) makes the reference divide by a
+    // zero volume (src/grid.h:96-101) and ask for a 31-level octree, i.e. it runs out of memory.
+    // Such a box is given a thickness of 0.1 % of its largest extent; boxes with positive extents
+    // are untouched, so every input the reference can build is built identically.
+    {
+        const vec3 e = grid_bb.extents();
+        const float widest = std::max(e.x, std::max(e.y, e.z));
+        const float pad = (widest > 0.0f ? widest : 1.0f) * 0.0005f;
+        if (!(e.x > 0.0f)) { grid_bb.min.x -= pad; grid_bb.max.x += pad; }
+        if (!(e.y > 0.0f)) { grid_bb.min.y -= pad; grid_bb.max.y += pad; }
+        if (!(e.z > 0.0f)) { grid_bb.min.z -= pad; grid_bb.max.z += pad; }
+    }
+
     // Cleary resolution, dims rounded up to even, box grown by 0.1 % per side (src/build.cu:728-737)
     ivec3 dims = compute_grid_dims(grid_bb, num_tris, top_density);
     dims.x += dims.x & 1; dims.y += dims.y & 1; dims.z += dims.z & 1;

@@ -81,7 +81,11 @@ struct tvec2 {
 
 template <typename T>
 struct tvec3 {
-    T x, y, z;
+    // r/g/b name the same storage: the front end's MTL parser writes colours through them
+    // (src/load_obj.cpp:279-301); the record stays three packed scalars.
+    union { T x, r; };
+    union { T y, g; };
+    union { T z, b; };
     HGB_HD tvec3() {}
     HGB_HD tvec3(T s) : x(s), y(s), z(s) {}
     HGB_HD tvec3(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {}

@@ -59,6 +59,20 @@ g++ -std=c++11 $CXXFLAGS -I"$HERE/sdl_stub" -I"$W" -c main.cpp -o main.o
 g++ -std=c++11 $CXXFLAGS -I"$W" -c load_obj.cpp -o load_obj.o
 g++ -o "$OUT/hagrid_ref" main.o load_obj.o build.o merge.o flatten.o expand.o compress.o mem_manager.o profile.o traverse.o \
     -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+# Drop-in check: the reference's UNMODIFIED front end (main.cpp, load_obj.cpp/.h) compiled against
+# THIS repository's headers (hagrid_b200/include/hagrid) and linked with THIS repository's kernels.
+# The three files are compiled from a scratch directory that holds nothing else, so every
+# "build.h"/"grid.h"/... they include resolves to our headers, not the reference's.
+OURS="$ROOT/hagrid_b200"
+if ls "$OURS"/_build/ray_traverse.o >/dev/null 2>&1; then
+  D=$(mktemp -d)
+  cp "$REF"/src/main.cpp "$REF"/src/load_obj.cpp "$REF"/src/load_obj.h "$D"/
+  (cd "$D" && g++ -std=c++11 $CXXFLAGS -I"$HERE/sdl_stub" -I"$OURS/include/hagrid" -c main.cpp -o main.o \
+           && g++ -std=c++11 $CXXFLAGS -I"$OURS/include/hagrid" -c load_obj.cpp -o load_obj.o)
+  g++ -o "$OUT/hagrid_dropin" "$D"/main.o "$D"/load_obj.o $(ls "$OURS"/_build/*.o | grep -v c_api.o) \
+      -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+  rm -rf "$D"
+fi
 # SASS of the reference traversal, for expression-shape comparison (not shipped in git)
 /usr/local/cuda/bin/cuobjdump -sass traverse_pid.o > "$OUT/traverse_pid.sass" 2>/dev/null || true
 echo "built: $(ls "$OUT")"

@@ -310,6 +310,13 @@ og_grid* og_build(const og_tri* tris, int n, float top_density, float snd_densit
         for (int k = 0; k < 3; k++) { lo[k] = sel_min(lo[k], tlo[3 * i + k]); hi[k] = sel_max(hi[k], thi[3 * i + k]); }
     }
     float ext[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+    {   /* outside the reference's domain: a flat scene box (zero volume, src/grid.h:96-101 divides by it) gets a
+           thickness of 0.1 % of its largest extent — same rule as hagrid_b200/csrc/grid_build.cu */
+        const float widest = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
+        const float pad = (widest > 0.0f ? widest : 1.0f) * 0.0005f;
+        for (int k = 0; k < 3; k++)
+            if (!(ext[k] > 0.0f)) { lo[k] -= pad; hi[k] += pad; ext[k] = hi[k] - lo[k]; }
+    }
     {
         const float volume = ext[0] * ext[1] * ext[2];
         const float ratio = cbrtf(top_density * n / volume);

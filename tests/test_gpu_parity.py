@@ -261,9 +261,14 @@ def test_rays_missing_the_grid_and_degenerate_rays(lib):
 
 def test_single_and_degenerate_triangles(lib):
     tris = scenes.make_tris([[0, 0, 0], [0, 0, 0]], [[1, 0, 0], [0, 0, 0]], [[0, 1, 0], [0, 0, 0]])   # second one is a point
+    from oracle import oracle
     for t in (tris[:1], tris):
         sc = Scene(t, lib=lib)
         sc.build_all(0.12, 2.4)
+        cpu = oracle.Grid.build(t, 0.12, 2.4)       # flat scene box: both sides apply the same thickness rule
+        cpu.merge(); cpu.flatten(); cpu.expand()
+        info, arrays = dump(sc)
+        assert grid_diff(info, arrays, (cpu.info(),) + cpu.arrays()) == []
         sc.setup_traversal()
         rays = np.zeros(2, dtype=RAY_DTYPE)
         rays["org"] = [(0.25, 0.25, 1.0), (2.0, 2.0, 1.0)]; rays["dir"] = (0, 0, -1); rays["tmax"] = 10.0

@@ -78,3 +78,19 @@ def test_grid_invariants(golden):
     assert sinfo["num_refs"] == int((n[n > 0] + 1).sum())
     assert np.array_equal(scells["begin"] < 0, n == 0)
     assert (srefs == -1).sum() == int((n > 0).sum())
+
+
+def test_flat_scene_box_is_given_a_thickness():
+    """All triangles in one axis-aligned plane: the reference divides by a zero volume (src/grid.h:96-101).
+    Oracle and product share one rule for this case (0.1 % of the widest extent); the hits must be right."""
+    from hagrid_b200 import RAY_DTYPE, scenes
+    tris = scenes.make_tris([[0, 0, 0], [0, 0, 0]], [[1, 0, 0], [0, 0, 0]], [[0, 1, 0], [0, 0, 0]])
+    for t in (tris[:1], tris):
+        grid = oracle.Grid.build(t, 0.12, 2.4)
+        grid.merge(); grid.flatten(); grid.expand()
+        info = grid.info()
+        assert info["bbox_max"][2] > info["bbox_min"][2] and info["shift"] < 8
+        rays = np.zeros(2, dtype=RAY_DTYPE)
+        rays["org"] = [(0.25, 0.25, 1.0), (2.0, 2.0, 1.0)]; rays["dir"] = (0, 0, -1); rays["tmax"] = 10.0
+        res = grid.traverse(t, rays, 1)
+        assert res["id"][0] == 0 and abs(res["t"][0] - 1.0) < 1e-6 and res["id"][1] == -1
