@@ -31,6 +31,8 @@ void traverse_grid_pid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* 
 #else
 // Extra entry points of this library (hagrid_b200/include/hagrid/traverse.h).
 void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays);
+void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays, Hit* host_hits, int num_rays,
+                        Ray* dev_rays, Hit* dev_hits, bool prim_ids);
 bool set_traversal_option(const char* key, int value);
 unsigned long long kernel_launch_count();
 #endif
@@ -91,6 +93,15 @@ static void release_grid(hgb_scene* s) {
     s->grid.cells = nullptr;
     s->grid.ref_ids = nullptr;
     s->grid.small_cells = nullptr;
+}
+
+// The traversal constants are per process (src/traverse.cu:7-12): remember which grid they describe so
+// that tracing another scene without a new hgb_setup_traversal is an error code, not a wild walk.
+static struct { const hgb_scene* scene; const void* entries; const void* cells; int shift; } g_setup = {nullptr, nullptr, nullptr, 0};
+
+static bool setup_matches(const hgb_scene* s) {
+    const void* cells = s->grid.small_cells ? static_cast<const void*>(s->grid.small_cells) : static_cast<const void*>(s->grid.cells);
+    return g_setup.scene == s && g_setup.entries == s->grid.entries && g_setup.cells == cells && g_setup.shift == s->grid.shift;
 }
 
 static void run_traverse(hgb_scene* s, const Ray* rays, Hit* hits, int n, int hit_mode) {
@@ -228,12 +239,17 @@ int hgb_setup_traversal(hgb_scene* s) {
 #ifdef HGB_REFERENCE_BUILD
     setup_traversal_pid(s->grid);
 #endif
+    g_setup.scene = s;
+    g_setup.entries = s->grid.entries;
+    g_setup.cells = s->grid.small_cells ? static_cast<const void*>(s->grid.small_cells) : static_cast<const void*>(s->grid.cells);
+    g_setup.shift = s->grid.shift;
     return 0;
 }
 
 int hgb_traverse_grid(hgb_scene* s, const void* dev_rays, void* dev_hits, int num_rays, int hit_mode) {
     if (!bind(s)) return -1;
     if (!s->grid.entries) return fail("traverse_grid: no grid");
+    if (!setup_matches(s)) return fail("traverse_grid: hgb_setup_traversal was not called for this grid");
     if (num_rays <= 0) return 0;
     run_traverse(s, static_cast<const Ray*>(dev_rays), static_cast<Hit*>(dev_hits), num_rays, hit_mode);
     return 0;
@@ -243,6 +259,7 @@ int hgb_traverse_timed(hgb_scene* s, const void* dev_rays, void* dev_hits, int n
                        int hit_mode, int warmup, int iters, float* ms_out) {
     if (!bind(s)) return -1;
     if (!s->grid.entries) return fail("traverse_timed: no grid");
+    if (!setup_matches(s)) return fail("traverse_timed: hgb_setup_traversal was not called for this grid");
     if (num_rays <= 0) return fail("traverse_timed: no rays");
     auto rays = static_cast<const Ray*>(dev_rays);
     auto hits = static_cast<Hit*>(dev_hits);
@@ -257,6 +274,7 @@ int hgb_traverse_timed(hgb_scene* s, const void* dev_rays, void* dev_hits, int n
 int hgb_traverse_grid_host(hgb_scene* s, const void* host_rays, void* host_hits, int num_rays, int hit_mode) {
     if (!bind(s)) return -1;
     if (!s->grid.entries) return fail("traverse_grid_host: no grid");
+    if (!setup_matches(s)) return fail("traverse_grid_host: hgb_setup_traversal was not called for this grid");
     if (num_rays <= 0) return 0;
     if (num_rays > s->frame_capacity) {
         s->mem.free(s->frame_rays);
@@ -265,9 +283,15 @@ int hgb_traverse_grid_host(hgb_scene* s, const void* host_rays, void* host_hits,
         s->frame_hits = s->mem.alloc<Hit>(num_rays);
         s->frame_capacity = num_rays;
     }
+#ifdef HGB_REFERENCE_BUILD
+    // the reference's frame, verbatim: blocking upload, launch, blocking download (src/main.cpp:599-613)
     s->mem.copy<Copy::HST_TO_DEV>(s->frame_rays, static_cast<const Ray*>(host_rays), num_rays);
     run_traverse(s, s->frame_rays, s->frame_hits, num_rays, hit_mode);
     s->mem.copy<Copy::DEV_TO_HST>(static_cast<Hit*>(host_hits), s->frame_hits, num_rays);
+#else
+    traverse_grid_host(s->grid, s->tris, static_cast<const Ray*>(host_rays), static_cast<Hit*>(host_hits), num_rays,
+                       s->frame_rays, s->frame_hits, hit_mode == HGB_HIT_PRIM_ID);
+#endif
     return 0;
 }
 

@@ -18,6 +18,8 @@
 //
 // The grid, the references and the triangles (tens of MB) live in the 126 MB
 // L2; compulsory HBM traffic is 32 B/ray in + 16 B/hit out.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -239,12 +241,12 @@ traverse_per_thread(const __grid_constant__ TraversalParams P,
                     const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                     const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                     const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
-                    const int* __restrict__ layout) {
+                    const int* __restrict__ layout, int host_width) {
     constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
     int id = threadIdx.x + blockDim.x * blockIdx.x;
     if (id >= num_rays) return;
-    if (layout) {
-        const int width = __ldg(layout);
+    {   // raster width: found on the device (layout word) or already known to the host
+        const int width = layout ? __ldg(layout) : host_width;
         if (width > 0) id = tiled_ray_index(id, width);
     }
     RayState r;
@@ -369,6 +371,12 @@ struct DeviceState {
     const void* seen_rays = nullptr; // buffer the layout belongs to
     int seen_count = -1;
     int num_sms = 0;
+    // host-buffer frames (traverse_grid_host): chunks round-robin over these streams
+    static constexpr int kStreams = 4;
+    cudaStream_t streams[kStreams] = {};
+    cudaEvent_t  stream_done[kStreams] = {};
+    cudaEvent_t  frame_start = nullptr;
+    int* stream_counters = nullptr;  // one persistent-kernel ray counter per stream (32-byte stride)
 };
 
 DeviceState& device_state() {
@@ -388,6 +396,16 @@ DeviceState& device_state() {
     return st;
 }
 
+void prepare_streams(DeviceState& st) {
+    if (st.frame_start) return;
+    for (int i = 0; i < DeviceState::kStreams; i++) {
+        HGB_CUDA(cudaStreamCreateWithFlags(&st.streams[i], cudaStreamNonBlocking));
+        HGB_CUDA(cudaEventCreateWithFlags(&st.stream_done[i], cudaEventDisableTiming));
+    }
+    HGB_CUDA(cudaEventCreateWithFlags(&st.frame_start, cudaEventDisableTiming));
+    HGB_CUDA(cudaMalloc(&st.stream_counters, DeviceState::kStreams * 32));
+}
+
 // 0: per thread, buffer order   1: persistent   2: per thread, re-tiled when a raster is detected
 // 3 (default): 2 for buffers that are (or may be) rasters, 1 once a buffer is known not to be one
 int g_variant = -1;
@@ -400,14 +418,47 @@ int traverse_variant() {
     return g_variant;
 }
 
+/// Enqueues one traversal launch on `stream`. variant 1 = persistent (needs `counter`), otherwise one
+/// thread per ray, re-tiled by the raster width in `layout[0]` (device) or `host_width`.
 template <typename CellT, bool kPrimId>
-void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
-    if (num_rays <= 0) return;
+void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays,
+             int variant, const int* layout, int host_width, int* counter, int num_sms, cudaStream_t stream) {
+    auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
+    if (variant == 1) {
+        static int occ = 0;
+        if (!occ) HGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traverse_persistent<CellT, kPrimId>, kBlockThreads, 0));
+        HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        const int blocks = min(num_sms * max(occ, 1), round_div(num_rays, kBlockThreads));
+        traverse_persistent<CellT, kPrimId><<<blocks, kBlockThreads, 0, stream>>>(
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, counter); count_launch();
+    } else {
+        traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128, 0, stream>>>(
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width); count_launch();
+    }
+}
+
+/// The traversal constants live in this translation unit, like the reference's __constant__s
+/// (src/traverse.cu:7-12): tracing a grid other than the one last given to setup_traversal would walk
+/// it with foreign dimensions (possibly forever), so that caller error is fatal here.
+void require_setup(const Grid& grid) {
     if (!g_params_set) {
         std::fprintf(stderr, "hagrid_b200: traverse_grid called before setup_traversal\n");
         std::abort();
     }
-    auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
+    const TraversalParams& P = g_params;
+    const bool same = P.shift == grid.shift && P.dims_x == (grid.dims.x << grid.shift) && P.dims_y == (grid.dims.y << grid.shift) &&
+                      P.dims_z == (grid.dims.z << grid.shift) && P.min_x == grid.bbox.min.x && P.min_y == grid.bbox.min.y &&
+                      P.min_z == grid.bbox.min.z && P.max_x == grid.bbox.max.x && P.max_y == grid.bbox.max.y && P.max_z == grid.bbox.max.z;
+    if (!same) {
+        std::fprintf(stderr, "hagrid_b200: traverse_grid called with a grid other than the one given to setup_traversal\n");
+        std::abort();
+    }
+}
+
+template <typename CellT, bool kPrimId>
+void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
+    if (num_rays <= 0) return;
+    require_setup(grid);
     DeviceState& st = device_state();
     int variant = traverse_variant();
     if (variant >= 2) {
@@ -423,18 +474,89 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
         }
         if (variant == 3) variant = *static_cast<volatile int*>(st.layout_host) == 0 ? 1 : 2;
     }
-    if (variant == 1) {
-        int occ = 0;
-        HGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traverse_persistent<CellT, kPrimId>, kBlockThreads, 0));
-        HGB_CUDA(cudaMemsetAsync(st.counter, 0, sizeof(int), 0));
-        const int blocks = min(st.num_sms * max(occ, 1), round_div(num_rays, kBlockThreads));
-        traverse_persistent<CellT, kPrimId><<<blocks, kBlockThreads>>>(
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, st.counter); count_launch();
-    } else {
-        traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128>>>(
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, variant == 2 ? st.layout : nullptr); count_launch();
+    enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, variant == 2 ? st.layout : nullptr, 0,
+                            st.counter, st.num_sms, 0);
+    HGB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// Host-buffer frames (the interactive loop of src/main.cpp:599-613: upload the rays, trace, download
+// the hits). The three steps of one frame are cut into chunks that travel round-robin over a few
+// streams, so the upload of chunk i+1, the traversal of chunk i and the download of chunk i-1 overlap;
+// PCIe is full duplex, so a frame costs about as long as its 32 B/ray upload alone.
+// ---------------------------------------------------------------------------
+
+/// Host mirror of detect_raster for a buffer in host memory: the row length W of a W x H raster of
+/// smoothly varying rays (W % 8 == 0, H % 4 == 0), else 0. Any answer is safe (the re-tiling is a
+/// bijection for every such W); the scan stops at the first row break, so it reads W rays, not n.
+int host_raster_width(const Ray* rays, int n) {
+    constexpr int kScan = 16384;
+    if (n < 4 * 64) return 0;
+    auto delta = [&](int i, float d[6]) {
+        const Ray& a = rays[i]; const Ray& b = rays[i - 1];
+        d[0] = a.org.x - b.org.x; d[1] = a.org.y - b.org.y; d[2] = a.org.z - b.org.z;
+        d[3] = a.dir.x - b.dir.x; d[4] = a.dir.y - b.dir.y; d[5] = a.dir.z - b.dir.z;
+    };
+    float step[6];
+    delta(1, step);
+    float tol = 0.0f;
+    for (int k = 0; k < 6; k++) tol = std::fmax(tol, std::fabs(step[k]));
+    tol *= 0.25f;
+    if (!(tol > 0.0f)) return 0;
+    auto continues = [&](int i) {
+        float d[6];
+        delta(i, d);
+        float err = 0.0f;
+        for (int k = 0; k < 6; k++) err = std::fmax(err, std::fabs(d[k] - step[k]));
+        return err <= tol;
+    };
+    const int limit = n < kScan ? n : kScan;
+    int width = 2;
+    while (width < limit && continues(width)) width++;
+    if (width >= limit || width < 64 || width % kTileW != 0 || n % width != 0 || (n / width) % kTileH != 0) return 0;
+    for (int k = 0; k < 62; k++)
+        if (!continues(width + 1 + k) || !continues(n - width + 1 + k)) return 0;
+    return width;
+}
+
+template <typename CellT, bool kPrimId>
+void launch_host_frame(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* host_rays, Hit* host_hits,
+                       int num_rays, Ray* dev_rays, Hit* dev_hits) {
+    if (num_rays <= 0) return;
+    require_setup(grid);
+    DeviceState& st = device_state();
+    prepare_streams(st);
+
+    int variant = traverse_variant();
+    int width = 0;
+    if (variant >= 2) {
+        width = host_raster_width(host_rays, num_rays);
+        variant = width > 0 ? 2 : (variant == 3 ? 1 : 0);
+    }
+    // chunk = whole 4-row tile bands of a raster, else whole blocks; at most 16 chunks of at least 32 K rays
+    const int granule = width > 0 ? width * kTileH : kBlockThreads;
+    const int units = round_div(num_rays, granule);
+    const int min_units = std::max(1, (1 << 15) / granule);
+    const int chunk_units = std::max(min_units, round_div(units, 16));
+    const long long chunk = (long long)chunk_units * granule;
+
+    HGB_CUDA(cudaEventRecord(st.frame_start, 0));           // frames are ordered after earlier default-stream work
+    for (int i = 0; i < DeviceState::kStreams; i++) HGB_CUDA(cudaStreamWaitEvent(st.streams[i], st.frame_start, 0));
+    int slot = 0;
+    for (long long begin = 0; begin < num_rays; begin += chunk, slot = (slot + 1) % DeviceState::kStreams) {
+        const int count = int(std::min<long long>(chunk, num_rays - begin));
+        cudaStream_t stream = st.streams[slot];
+        HGB_CUDA(cudaMemcpyAsync(dev_rays + begin, host_rays + begin, sizeof(Ray) * size_t(count), cudaMemcpyHostToDevice, stream));
+        enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, dev_hits + begin, count, variant, nullptr, width,
+                                st.stream_counters + slot * 8, st.num_sms, stream);
+        HGB_CUDA(cudaMemcpyAsync(host_hits + begin, dev_hits + begin, sizeof(Hit) * size_t(count), cudaMemcpyDeviceToHost, stream));
     }
     HGB_CUDA(cudaGetLastError());
+    for (int i = 0; i < DeviceState::kStreams; i++) {
+        HGB_CUDA(cudaEventRecord(st.stream_done[i], st.streams[i]));
+        HGB_CUDA(cudaStreamWaitEvent(0, st.stream_done[i], 0));   // a timer on the default stream brackets the frame
+    }
+    for (int i = 0; i < DeviceState::kStreams; i++) HGB_CUDA(cudaStreamSynchronize(st.streams[i]));   // hits are in host memory
 }
 
 template <bool kPrimId>
@@ -473,6 +595,17 @@ void traverse_grid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits
 
 void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
     dispatch<true>(grid, tris, rays, hits, num_rays);
+}
+
+void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays, Hit* host_hits, int num_rays,
+                        Ray* dev_rays, Hit* dev_hits, bool prim_ids) {
+    if (grid.small_cells) {
+        if (prim_ids) launch_host_frame<SmallCell, true>(grid, grid.small_cells, tris, host_rays, host_hits, num_rays, dev_rays, dev_hits);
+        else          launch_host_frame<SmallCell, false>(grid, grid.small_cells, tris, host_rays, host_hits, num_rays, dev_rays, dev_hits);
+    } else {
+        if (prim_ids) launch_host_frame<Cell, true>(grid, grid.cells, tris, host_rays, host_hits, num_rays, dev_rays, dev_hits);
+        else          launch_host_frame<Cell, false>(grid, grid.cells, tris, host_rays, host_hits, num_rays, dev_rays, dev_hits);
+    }
 }
 
 } // namespace hagrid

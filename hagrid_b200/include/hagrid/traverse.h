@@ -18,6 +18,14 @@ void traverse_grid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits
 /// documented in src/ray.h:22. Not part of the reference API.
 void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays);
 
+/// One interactive frame with HOST buffers (the loop body of src/main.cpp:599-613): uploads the rays,
+/// traces them, downloads the hits; returns when `host_hits` is complete. Upload, traversal and download
+/// are pipelined in chunks over several streams (fastest with page-locked host buffers; pageable ones
+/// work). `dev_rays`/`dev_hits` are device staging buffers of `num_rays` elements owned by the caller.
+/// Not part of the reference API.
+void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays, Hit* host_hits, int num_rays,
+                        Ray* dev_rays, Hit* dev_hits, bool prim_ids);
+
 /// Tuning switches ("traverse_variant": 0 = one thread per ray, 1 = persistent
 /// phase-scheduled warps). Returns false for unknown keys.
 bool set_traversal_option(const char* key, int value);

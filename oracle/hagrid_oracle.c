@@ -158,7 +158,7 @@ static void traverse_one(const og_grid* g, const og_tri* tris, const og_ray* ray
     const float tstart = fmaxf(fmaxf(t0[0], fmaxf(t0[1], t0[2])), ray->tmin);
     const float tend = fminf(fminf(t1[0], fminf(t1[1], t1[2])), ray->tmax);
     og_hit hit = {-1, ray->tmax, 0, 0};
-    int steps = 0;
+    int steps = 0, visited = 0;
     if (!(tstart > tend)) {
         int voxel[3];
         for (int k = 0; k < 3; k++)
@@ -175,6 +175,7 @@ static void traverse_one(const og_grid* g, const og_tri* tris, const og_ray* ray
                 for (int k = 0; k < 3; k++) { cmin[k] = c->min[k]; cmax[k] = c->max[k]; }
                 begin = c->begin; end = c->end;
             }
+            visited++;
             int point[3]; float tc[3];
             for (int k = 0; k < 3; k++) {
                 point[k] = dir[k] >= 0.0f ? cmax[k] : cmin[k];
@@ -203,11 +204,12 @@ static void traverse_one(const og_grid* g, const og_tri* tris, const og_ray* ray
                 break;
         }
     }
-    if (!prim_id_mode) hit.id = steps;      /* src/traverse.cu:93 */
+    if (prim_id_mode != 1) hit.id = steps;  /* src/traverse.cu:93 */
+    if (prim_id_mode == 2) hit.u = (float)visited;   /* statistics for DESIGN.md: cells visited (not a reference output) */
     *out = hit;
 }
 
-/* mode 0: Hit.id = step count (reference verbatim), 1: primitive id. `threads` worker
+/* mode 0: Hit.id = step count (reference verbatim), 1: primitive id, 2: mode 0 plus Hit.u = cells visited. `threads` worker
  * threads pull chunks of 256 rays from a shared counter (pthreads; used by bench.py's
  * cpu_baseline leg to occupy all host cores). */
 typedef struct {

@@ -309,6 +309,54 @@ def test_host_buffer_entry_point(lib):
     sc.close()
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_frames_are_pipelined_without_changing_hits(lib, sponza, pinned):
+    """hgb_traverse_grid_host cuts a frame into chunks over several streams: raster frames (chunks are
+    4-row tile bands), incoherent frames, ragged sizes and sizes below one chunk give the hits of one
+    plain device launch, from pageable and from page-locked host buffers."""
+    import torch
+    tris, sc, _ = sponza
+    sc.setup_traversal()          # the traversal constants are per process, like the reference's (src/traverse.cu:7-12)
+    lo, hi = scenes.scene_bbox(tris)
+    eye = 0.5 * (lo + hi)
+    frames = [scenes.primary_rays(eye, eye + np.array([0.3, 0.0, 1.0], np.float32), (0, 1, 0), 60.0, 1280, 720, 1e4),
+              scenes.random_rays(tris, 700001, seed=12),
+              scenes.primary_rays(eye, eye + np.array([0.0, 0.1, 1.0], np.float32), (0, 1, 0), 60.0, 64, 8, 1e4),
+              scenes.random_rays(tris, 77, seed=13)]
+    for rays in frames:
+        n = rays.shape[0]
+        want = sc.trace(rays, HIT_PRIM_ID)
+        for mode in (HIT_PRIM_ID, HIT_STEPS):
+            if pinned:
+                h_rays = torch.from_numpy(rays.view(np.float32).reshape(n, 8)).pin_memory()
+                h_hits = torch.zeros((n, 4), dtype=torch.float32).pin_memory()
+                lib.check(lib.dll.hgb_traverse_grid_host(sc._h, h_rays.data_ptr(), h_hits.data_ptr(), n, mode), "host frame")
+                got = h_hits.numpy().view(want.dtype).reshape(-1)
+            else:
+                got = sc.traverse_host(rays, mode)
+            ref = want if mode == HIT_PRIM_ID else sc.trace(rays, HIT_STEPS)
+            assert np.array_equal(got["id"], ref["id"]) and np.array_equal(got["t"].view(np.uint32), ref["t"].view(np.uint32))
+
+
+def test_tracing_a_grid_without_its_setup_is_an_error(lib):
+    """The traversal constants are per process (src/traverse.cu:7-12); the C ABI refuses to walk a grid
+    with another grid's constants instead of letting the kernel run wild."""
+    from hagrid_b200 import HagridError
+    g = Golden("cornell32")
+    a, b = Scene(g.tris, lib=lib), Scene(scenes.small_mixed(500, seed=2), lib=lib)
+    a.build_all(g.top_density, g.snd_density); b.build_all(0.12, 2.4)
+    a.setup_traversal()
+    assert a.trace(g.rays, HIT_PRIM_ID).shape[0] == g.rays.shape[0]
+    with pytest.raises(HagridError):
+        b.trace(g.rays, HIT_PRIM_ID)
+    a.build_all(g.top_density, g.snd_density)          # rebuilt: the old constants no longer describe it
+    with pytest.raises(HagridError):
+        a.trace(g.rays, HIT_PRIM_ID)
+    a.setup_traversal()
+    assert np.array_equal(a.trace(g.rays, HIT_PRIM_ID)["id"], g.hits["hits_cell_ids"]["id"])
+    a.close(); b.close()
+
+
 def test_buffer_pool_reuse(lib):
     sc = Scene(scenes.cornell32(), keep_alive=True, lib=lib)
     a = sc.device_alloc(1 << 20)
