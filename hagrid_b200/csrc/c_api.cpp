@@ -49,10 +49,11 @@ struct hgb_scene {
     Ray* frame_rays;
     Hit* frame_hits;
     int frame_capacity;
+    unsigned long long grid_epoch;      // bumped by everything that changes the grid
 
     hgb_scene(int dev, bool keep)
         : mem(keep), tris(nullptr), num_tris(0), device(dev),
-          frame_rays(nullptr), frame_hits(nullptr), frame_capacity(0)
+          frame_rays(nullptr), frame_hits(nullptr), frame_capacity(0), grid_epoch(0)
     {
         grid.entries = nullptr;
         grid.ref_ids = nullptr;
@@ -82,6 +83,7 @@ static bool bind(const hgb_scene* scene) {
 }
 
 static void release_grid(hgb_scene* s) {
+    s->grid_epoch++;
     // main.cpp:496-498 frees exactly these three; small_cells is leaked by the
     // reference across rebuilds (build.cu:755). Freeing it here is harmless for
     // both builds because it always comes from the same MemManager.
@@ -97,12 +99,9 @@ static void release_grid(hgb_scene* s) {
 
 // The traversal constants are per process (src/traverse.cu:7-12): remember which grid they describe so
 // that tracing another scene without a new hgb_setup_traversal is an error code, not a wild walk.
-static struct { const hgb_scene* scene; const void* entries; const void* cells; int shift; } g_setup = {nullptr, nullptr, nullptr, 0};
+static struct { const hgb_scene* scene; unsigned long long epoch; } g_setup = {nullptr, 0};
 
-static bool setup_matches(const hgb_scene* s) {
-    const void* cells = s->grid.small_cells ? static_cast<const void*>(s->grid.small_cells) : static_cast<const void*>(s->grid.cells);
-    return g_setup.scene == s && g_setup.entries == s->grid.entries && g_setup.cells == cells && g_setup.shift == s->grid.shift;
-}
+static bool setup_matches(const hgb_scene* s) { return g_setup.scene == s && g_setup.epoch == s->grid_epoch; }
 
 static void run_traverse(hgb_scene* s, const Ray* rays, Hit* hits, int n, int hit_mode) {
     if (hit_mode == HGB_HIT_PRIM_ID) {
@@ -189,6 +188,7 @@ int hgb_build_grid(hgb_scene* s, float top_density, float snd_density) {
 int hgb_merge_grid(hgb_scene* s, float alpha) {
     if (!bind(s)) return -1;
     if (!s->grid.cells) return fail("merge_grid: no uncompressed grid");
+    s->grid_epoch++;
     merge_grid(s->mem, s->grid, alpha);
     return 0;
 }
@@ -196,6 +196,7 @@ int hgb_merge_grid(hgb_scene* s, float alpha) {
 int hgb_flatten_grid(hgb_scene* s) {
     if (!bind(s)) return -1;
     if (!s->grid.entries) return fail("flatten_grid: no grid");
+    s->grid_epoch++;
     flatten_grid(s->mem, s->grid);
     return 0;
 }
@@ -203,6 +204,7 @@ int hgb_flatten_grid(hgb_scene* s) {
 int hgb_expand_grid(hgb_scene* s, int iters) {
     if (!bind(s)) return -1;
     if (!s->grid.cells) return fail("expand_grid: no uncompressed grid");
+    s->grid_epoch++;
     expand_grid(s->mem, s->grid, s->tris, iters);
     return 0;
 }
@@ -210,6 +212,7 @@ int hgb_expand_grid(hgb_scene* s, int iters) {
 int hgb_compress_grid(hgb_scene* s) {
     if (!bind(s)) return -1;
     if (!s->grid.cells) return fail("compress_grid: no uncompressed grid");
+    s->grid_epoch++;
     return compress_grid(s->mem, s->grid) ? 1 : 0;
 }
 
@@ -240,9 +243,7 @@ int hgb_setup_traversal(hgb_scene* s) {
     setup_traversal_pid(s->grid);
 #endif
     g_setup.scene = s;
-    g_setup.entries = s->grid.entries;
-    g_setup.cells = s->grid.small_cells ? static_cast<const void*>(s->grid.small_cells) : static_cast<const void*>(s->grid.cells);
-    g_setup.shift = s->grid.shift;
+    g_setup.epoch = s->grid_epoch;
     return 0;
 }
 
