@@ -154,6 +154,7 @@ hgb_scene* hgb_scene_create(int device, int keep_alive) {
 
 void hgb_scene_destroy(hgb_scene* s) {
     if (!s) return;
+    if (g_setup.scene == s) g_setup.scene = nullptr;
     if (bind(s)) {
         cudaDeviceSynchronize();
         release_grid(s);

@@ -73,6 +73,18 @@ __device__ __forceinline__ float4 ldg4(const void* p) { return __ldg(reinterpret
 __device__ __forceinline__ int4   ldg4i(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
 __device__ __forceinline__ uint4  ldg4u(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+/// Streaming accesses: every ray is read once and every hit written once, so neither should displace
+/// the grid and the triangles from L1 (the loads skip L1 allocation, the stores are evict-first).
+__device__ __forceinline__ float4 ldg4_stream(const void* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg4_stream(void* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 struct CellBox {
     int min_x, min_y, min_z, begin;
     int max_x, max_y, max_z, end;     // `end` < 0: sentinel-terminated list (SmallCell)

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "device_math.cuh"
 #include "runtime.h"
@@ -93,8 +94,8 @@ __device__ __forceinline__ void intersect_tri(RayState& r, const Tri* __restrict
 /// (src/traverse.cu:36-54). Returns false when the ray misses the grid.
 __device__ __forceinline__ bool start_ray(RayState& r, const TraversalParams& P, const Ray* __restrict__ rays, int id) {
     using namespace dev;
-    const float4 a = ldg4(reinterpret_cast<const float4*>(rays + id) + 0);
-    const float4 b = ldg4(reinterpret_cast<const float4*>(rays + id) + 1);
+    const float4 a = ldg4_stream(reinterpret_cast<const float4*>(rays + id) + 0);
+    const float4 b = ldg4_stream(reinterpret_cast<const float4*>(rays + id) + 1);
     r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tmin = a.w;
     r.dx = b.x; r.dy = b.y; r.dz = b.z;
     r.ix = safe_rcp(b.x); r.iy = safe_rcp(b.y); r.iz = safe_rcp(b.z);
@@ -159,8 +160,7 @@ __device__ __forceinline__ bool outside(const RayState& r, const TraversalParams
 template <bool kPrimId>
 __device__ __forceinline__ void finish_ray(const RayState& r, Hit* __restrict__ hits, int id) {
     // u = v = 0: the reference never defines COMPUTE_UVS (src/prims.h:285-288)
-    *reinterpret_cast<float4*>(hits + id) =
-        make_float4(__int_as_float(kPrimId ? r.hit_id : r.steps), r.hit_t, 0.0f, 0.0f);
+    dev::stg4_stream(hits + id, make_float4(__int_as_float(kPrimId ? r.hit_id : r.steps), r.hit_t, 0.0f, 0.0f));
 }
 
 // ---------------------------------------------------------------------------
@@ -280,6 +280,118 @@ traverse_per_thread(const __grid_constant__ TraversalParams P,
 }
 
 // ---------------------------------------------------------------------------
+// Kernel A2: resident warps pull 32-ray tiles from a global counter (coherent buffers). Same per-ray
+// loop as kernel A; what changes is residency: a block of kernel A keeps its four warp slots until its
+// slowest warp is done (61 % achieved occupancy in ncu against 75 % theoretical), here a warp that is
+// done takes the next tile, so every warp slot of the SM stays busy until the counter runs out.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int tiled_ray_index_nodiv(int tile, int lane, int width) {
+    // tile / (width / 8) by a float estimate and one fix-up step each way (tile < 2^24 keeps it within +-1)
+    const int per_row = width >> 3;
+    int ty = __float2int_rz(__int2float_rn(tile) * dev::rcp(__int2float_rn(per_row)));
+    int tx = tile - ty * per_row;
+    if (tx < 0) { ty--; tx += per_row; }
+    if (tx >= per_row) { ty++; tx -= per_row; }
+    return (ty * kTileH + (lane >> 3)) * width + tx * kTileW + (lane & 7);
+}
+
+template <typename CellT, bool kPrimId>
+__device__ __forceinline__ void trace_one(const TraversalParams& P, const uint32_t* __restrict__ entries,
+                                          const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
+                                          const Tri* __restrict__ tris, const Ray* __restrict__ rays,
+                                          Hit* __restrict__ hits, int id) {
+    constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
+    RayState r;
+    if (start_ray(r, P, rays, id)) {
+        while (true) {
+            dev::CellBox cell;
+            const float texit = enter_cell(r, P, entries, cells, cell);
+            if (kSentinel) {
+                int cur = cell.begin;
+                int ref = cur >= 0 ? __ldg(ref_ids + cur++) : -1;
+                while (ref >= 0) {
+                    const int next = __ldg(ref_ids + cur++);
+                    intersect_tri(r, tris, ref);
+                    ref = next;
+                }
+                r.steps += 1 + (cur - cell.begin);
+            } else {
+                int cur = cell.begin;
+                int ref = cur < cell.end ? __ldg(ref_ids + cur++) : -1;
+                while (ref >= 0) {
+                    const int next = cur < cell.end ? __ldg(ref_ids + cur++) : -1;
+                    intersect_tri(r, tris, ref);
+                    ref = next;
+                }
+                r.steps += 1 + (cell.end - cell.begin);
+            }
+            if (r.hit_t <= texit) break;
+            // left the grid? (unsigned compare folds the < 0 test)
+            if ((unsigned(r.vx) >= unsigned(P.dims_x)) | (unsigned(r.vy) >= unsigned(P.dims_y)) | (unsigned(r.vz) >= unsigned(P.dims_z))) break;
+        }
+    }
+    finish_ray<kPrimId>(r, hits, id);
+}
+
+constexpr int kTileBlock = 128;
+
+/// ptxas re-loads kernel parameters from the constant bank inside the hot loops (about one issue slot in
+/// ten) instead of keeping them in registers; it sees through arithmetic identities and through shuffles
+/// of uniform values. A volatile shared-memory load is executed exactly once, so a parameter that took
+/// the detour through shared memory has to stay in a register.
+/// kHoist: 0 = leave it to ptxas, 1 = pointers and integers, 2 = the float constants too.
+struct HoistBox {
+    unsigned long long ptr[4];
+    int   i[6];
+    float f[9];
+};
+
+template <typename CellT, bool kPrimId, int kMinBlocks, int kHoist>
+__global__ void __launch_bounds__(kTileBlock, kMinBlocks)
+traverse_tiles(const __grid_constant__ TraversalParams P0,
+               const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
+               const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
+               const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
+               const int* __restrict__ layout, int host_width, int* __restrict__ next_tile) {
+    constexpr unsigned kAll = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    TraversalParams P = P0;
+    if (kHoist >= 1) {
+        __shared__ HoistBox box;
+        if (threadIdx.x == 0) {
+            box.ptr[0] = reinterpret_cast<unsigned long long>(entries); box.ptr[1] = reinterpret_cast<unsigned long long>(cells);
+            box.ptr[2] = reinterpret_cast<unsigned long long>(ref_ids); box.ptr[3] = reinterpret_cast<unsigned long long>(tris);
+            box.i[0] = P.dims_x; box.i[1] = P.dims_y; box.i[2] = P.dims_z; box.i[3] = P.top_x; box.i[4] = P.top_y; box.i[5] = P.shift;
+            box.f[0] = P.min_x; box.f[1] = P.min_y; box.f[2] = P.min_z; box.f[3] = P.cell_x; box.f[4] = P.cell_y; box.f[5] = P.cell_z;
+            box.f[6] = P.inv_x; box.f[7] = P.inv_y; box.f[8] = P.inv_z;
+        }
+        __syncthreads();
+        const volatile HoistBox& vb = box;
+        entries = reinterpret_cast<const uint32_t*>(vb.ptr[0]); cells = reinterpret_cast<const CellT*>(vb.ptr[1]);
+        ref_ids = reinterpret_cast<const int*>(vb.ptr[2]); tris = reinterpret_cast<const Tri*>(vb.ptr[3]);
+        P.dims_x = vb.i[0]; P.dims_y = vb.i[1]; P.dims_z = vb.i[2]; P.top_x = vb.i[3]; P.top_y = vb.i[4]; P.shift = vb.i[5];
+        if (kHoist >= 2) {
+            P.min_x = vb.f[0]; P.min_y = vb.f[1]; P.min_z = vb.f[2]; P.cell_x = vb.f[3]; P.cell_y = vb.f[4]; P.cell_z = vb.f[5];
+            P.inv_x = vb.f[6]; P.inv_y = vb.f[7]; P.inv_z = vb.f[8];
+        }
+    }
+    const int width = layout ? __ldg(layout) : host_width;
+    const int num_tiles = (num_rays + 31) >> 5;
+    const int first_dynamic = gridDim.x * (kTileBlock / 32);
+    int tile = blockIdx.x * (kTileBlock / 32) + (threadIdx.x >> 5);
+    while (tile < num_tiles) {
+        int id = tile * 32 + lane;
+        if (id < num_rays) {
+            if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
+            trace_one<CellT, kPrimId>(P, entries, cells, ref_ids, tris, rays, hits, id);
+        }
+        __syncwarp();
+        if (lane == 0) tile = first_dynamic + atomicAdd(next_tile, 1);
+        tile = __shfl_sync(kAll, tile, 0);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Kernel B: persistent warps, phase-scheduled (incoherent buffers).
 // ---------------------------------------------------------------------------
 constexpr int kBlockThreads = 128;
@@ -371,12 +483,14 @@ struct DeviceState {
     const void* seen_rays = nullptr; // buffer the layout belongs to
     int seen_count = -1;
     int num_sms = 0;
-    // host-buffer frames (traverse_grid_host): chunks round-robin over these streams
-    static constexpr int kStreams = 4;
-    cudaStream_t streams[kStreams] = {};
+    // host-buffer frames (traverse_grid_host): one upload stream, one download stream, two traversal streams
+    static constexpr int kStreams = 4, kMaxChunks = 64;
+    cudaStream_t streams[kStreams] = {};            // 0 = upload, 1 = download, 2 and 3 = traversal
+    cudaEvent_t  uploaded[kMaxChunks] = {};
+    cudaEvent_t  traced[kMaxChunks] = {};
     cudaEvent_t  stream_done[kStreams] = {};
     cudaEvent_t  frame_start = nullptr;
-    int* stream_counters = nullptr;  // one persistent-kernel ray counter per stream (32-byte stride)
+    int* stream_counters = nullptr;  // ray counter of the persistent kernel, one per traversal stream (32-byte stride)
 };
 
 DeviceState& device_state() {
@@ -402,13 +516,20 @@ void prepare_streams(DeviceState& st) {
         HGB_CUDA(cudaStreamCreateWithFlags(&st.streams[i], cudaStreamNonBlocking));
         HGB_CUDA(cudaEventCreateWithFlags(&st.stream_done[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < DeviceState::kMaxChunks; i++) {
+        HGB_CUDA(cudaEventCreateWithFlags(&st.uploaded[i], cudaEventDisableTiming));
+        HGB_CUDA(cudaEventCreateWithFlags(&st.traced[i], cudaEventDisableTiming));
+    }
     HGB_CUDA(cudaEventCreateWithFlags(&st.frame_start, cudaEventDisableTiming));
-    HGB_CUDA(cudaMalloc(&st.stream_counters, DeviceState::kStreams * 32));
+    HGB_CUDA(cudaMalloc(&st.stream_counters, 64));
 }
 
 // 0: per thread, buffer order   1: persistent   2: per thread, re-tiled when a raster is detected
 // 3 (default): 2 for buffers that are (or may be) rasters, 1 once a buffer is known not to be one
 int g_variant = -1;
+
+// Host-buffer frames: rays per full-size chunk (tuned on B200/PCIe 5: ~350 K rays = 11 MB up, 5.6 MB down)
+int g_host_frame_chunk = 384 * 1024;
 
 int traverse_variant() {
     if (g_variant < 0) {
@@ -424,7 +545,26 @@ template <typename CellT, bool kPrimId>
 void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays,
              int variant, const int* layout, int host_width, int* counter, int num_sms, cudaStream_t stream) {
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
-    if (variant == 1) {
+    if (variant >= 4) {
+        // tile-pulling resident warps; experiment matrix: registers allowed x parameter hoisting
+        //   4: 12 blocks/SM (<=40 regs)   5: 10 (<=51)   6: 8 (<=64)          ... ptxas places the constants
+        //   7: 10 blocks/SM, pointers+ints hoisted   8: 8 blocks/SM, pointers+ints   9: 8 blocks/SM, everything
+        HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        static const int kPerSm[] = {12, 10, 8, 10, 8, 8};
+        const int blocks = min(num_sms * kPerSm[min(variant, 9) - 4], round_div(num_rays, kTileBlock));
+#define HGB_TILES(MINB, HOIST) traverse_tiles<CellT, kPrimId, MINB, HOIST><<<blocks, kTileBlock, 0, stream>>>( \
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, counter)
+        switch (variant) {
+            case 4: HGB_TILES(12, 0); break;
+            case 5: HGB_TILES(10, 0); break;
+            case 6: HGB_TILES(8, 0); break;
+            case 7: HGB_TILES(10, 1); break;
+            case 8: HGB_TILES(8, 1); break;
+            default: HGB_TILES(8, 2); break;
+        }
+#undef HGB_TILES
+        count_launch();
+    } else if (variant == 1) {
         static int occ = 0;
         if (!occ) HGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traverse_persistent<CellT, kPrimId>, kBlockThreads, 0));
         HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
@@ -474,7 +614,7 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
         }
         if (variant == 3) variant = *static_cast<volatile int*>(st.layout_host) == 0 ? 1 : 2;
     }
-    enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, variant == 2 ? st.layout : nullptr, 0,
+    enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, variant >= 2 ? st.layout : nullptr, 0,
                             st.counter, st.num_sms, 0);
     HGB_CUDA(cudaGetLastError());
 }
@@ -533,23 +673,38 @@ void launch_host_frame(const Grid& grid, const CellT* cells, const Tri* tris, co
         width = host_raster_width(host_rays, num_rays);
         variant = width > 0 ? 2 : (variant == 3 ? 1 : 0);
     }
-    // chunk = whole 4-row tile bands of a raster, else whole blocks; at most 16 chunks of at least 32 K rays
+    // Chunks are whole 4-row tile bands of a raster, else whole blocks. Full-size chunks keep the copy
+    // engines busy with few, large transfers; the last one is split 1/2, 1/4, 1/4 because nothing
+    // overlaps the final traversal + download.
     const int granule = width > 0 ? width * kTileH : kBlockThreads;
-    const int units = round_div(num_rays, granule);
-    const int min_units = std::max(1, (1 << 15) / granule);
-    const int chunk_units = std::max(min_units, round_div(units, 16));
-    const long long chunk = (long long)chunk_units * granule;
+    long long full = std::max<long long>(granule, (long long)round_div(g_host_frame_chunk, granule) * granule);
+    full = std::max<long long>(full, (long long)round_div(round_div(num_rays, DeviceState::kMaxChunks - 4), granule) * granule);
+    std::vector<int> sizes;
+    {
+        long long rest = num_rays;
+        while (rest > full + full / 2) { sizes.push_back(int(full)); rest -= full; }
+        const long long half = std::min<long long>(rest, (long long)round_div(int(rest / 2), granule) * granule);
+        const long long quarter = std::min<long long>(rest - half, (long long)round_div(int(rest / 4), granule) * granule);
+        if (half > 0) sizes.push_back(int(half));
+        if (quarter > 0) sizes.push_back(int(quarter));
+        if (rest - half - quarter > 0) sizes.push_back(int(rest - half - quarter));
+    }
 
+    cudaStream_t up = st.streams[0], down = st.streams[1];
     HGB_CUDA(cudaEventRecord(st.frame_start, 0));           // frames are ordered after earlier default-stream work
     for (int i = 0; i < DeviceState::kStreams; i++) HGB_CUDA(cudaStreamWaitEvent(st.streams[i], st.frame_start, 0));
-    int slot = 0;
-    for (long long begin = 0; begin < num_rays; begin += chunk, slot = (slot + 1) % DeviceState::kStreams) {
-        const int count = int(std::min<long long>(chunk, num_rays - begin));
-        cudaStream_t stream = st.streams[slot];
-        HGB_CUDA(cudaMemcpyAsync(dev_rays + begin, host_rays + begin, sizeof(Ray) * size_t(count), cudaMemcpyHostToDevice, stream));
+    long long begin = 0;
+    for (size_t c = 0; c < sizes.size(); begin += sizes[c], c++) {
+        const int count = sizes[c];
+        cudaStream_t run = st.streams[2 + (c & 1)];      // consecutive traversals may overlap (tails of incoherent chunks)
+        HGB_CUDA(cudaMemcpyAsync(dev_rays + begin, host_rays + begin, sizeof(Ray) * size_t(count), cudaMemcpyHostToDevice, up));
+        HGB_CUDA(cudaEventRecord(st.uploaded[c], up));
+        HGB_CUDA(cudaStreamWaitEvent(run, st.uploaded[c], 0));
         enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, dev_hits + begin, count, variant, nullptr, width,
-                                st.stream_counters + slot * 8, st.num_sms, stream);
-        HGB_CUDA(cudaMemcpyAsync(host_hits + begin, dev_hits + begin, sizeof(Hit) * size_t(count), cudaMemcpyDeviceToHost, stream));
+                                st.stream_counters + (c & 1) * 8, st.num_sms, run);
+        HGB_CUDA(cudaEventRecord(st.traced[c], run));
+        HGB_CUDA(cudaStreamWaitEvent(down, st.traced[c], 0));
+        HGB_CUDA(cudaMemcpyAsync(host_hits + begin, dev_hits + begin, sizeof(Hit) * size_t(count), cudaMemcpyDeviceToHost, down));
     }
     HGB_CUDA(cudaGetLastError());
     for (int i = 0; i < DeviceState::kStreams; i++) {
@@ -586,6 +741,7 @@ void setup_traversal(const Grid& grid) {
 
 bool set_traversal_option(const char* key, int value) {
     if (!std::strcmp(key, "traverse_variant")) { g_variant = value; return true; }
+    if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk = value > 0 ? value : 384 * 1024; return true; }
     return false;
 }
 

@@ -139,6 +139,11 @@ static void intersect_tri(const og_tri* t, const float* org, const float* dir, f
 }
 
 /* ------------------------------------------------------------------ traversal (src/traverse.cu:28-95) */
+/* statistics only (tools/warp_sim.py): when set, the reference count of every visited cell is appended here */
+static __thread short* og_record = NULL;
+static __thread int* og_record_cells = NULL;
+static __thread int og_record_max = 0;
+
 static void traverse_one(const og_grid* g, const og_tri* tris, const og_ray* ray, og_hit* out, int prim_id_mode) {
     /* constants as setup_traversal computes them on the host (src/traverse.cu:97-101) */
     const int dims[3] = {g->dims[0] << g->shift, g->dims[1] << g->shift, g->dims[2] << g->shift};
@@ -175,6 +180,8 @@ static void traverse_one(const og_grid* g, const og_tri* tris, const og_ray* ray
                 for (int k = 0; k < 3; k++) { cmin[k] = c->min[k]; cmax[k] = c->max[k]; }
                 begin = c->begin; end = c->end;
             }
+            if (og_record_cells && visited < og_record_max) og_record_cells[visited] = cell_id;
+            if (og_record && visited < og_record_max) og_record[visited] = (short)(g->compressed ? -2 : imin(end - begin, 32767));
             visited++;
             int point[3]; float tc[3];
             for (int k = 0; k < 3; k++) {
@@ -227,6 +234,30 @@ static void* traverse_worker(void* arg) {
         for (int i = begin; i < end; i++) traverse_one(job->g, job->tris, job->rays + i, job->hits + i, job->mode);
     }
     return NULL;
+}
+
+/* statistics only: counts[i * max_steps + k] = references in the k-th cell ray i visits, -1 after the last one */
+void og_traverse_record(const og_grid* g, const og_tri* tris, const og_ray* rays, short* counts, int max_steps, int num_rays) {
+    og_init();
+    for (int i = 0; i < num_rays; i++) {
+        og_hit h;
+        for (int k = 0; k < max_steps; k++) counts[(size_t)i * max_steps + k] = -1;
+        og_record = counts + (size_t)i * max_steps; og_record_max = max_steps;
+        traverse_one(g, tris, rays + i, &h, 1);
+    }
+    og_record = NULL;
+}
+
+/* statistics only: cells[i * max_steps + k] = index of the k-th cell ray i visits, -1 after the last one */
+void og_traverse_record_cells(const og_grid* g, const og_tri* tris, const og_ray* rays, int* cells, int max_steps, int num_rays) {
+    og_init();
+    for (int i = 0; i < num_rays; i++) {
+        og_hit h;
+        for (int k = 0; k < max_steps; k++) cells[(size_t)i * max_steps + k] = -1;
+        og_record_cells = cells + (size_t)i * max_steps; og_record_max = max_steps;
+        traverse_one(g, tris, rays + i, &h, 1);
+    }
+    og_record_cells = NULL;
 }
 
 void og_traverse(const og_grid* g, const og_tri* tris, const og_ray* rays, og_hit* hits, int num_rays, int mode, int threads) {

@@ -52,6 +52,8 @@ def dll():
         _dll.og_compress.argtypes = [P]
         _dll.og_compress.restype = C.c_int
         _dll.og_traverse.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _dll.og_traverse_record.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        _dll.og_traverse_record_cells.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return _dll
 
 
@@ -108,3 +110,17 @@ class Grid:
         hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
         dll().og_traverse(self.ptr, tris.ctypes.data, rays.ctypes.data, hits.ctypes.data, rays.shape[0], mode, threads)
         return hits
+
+    def record(self, tris: np.ndarray, rays: np.ndarray, max_steps: int = 128) -> np.ndarray:
+        """Statistics: (num_rays, max_steps) int16, reference count of each visited cell, -1 padded."""
+        tris = np.ascontiguousarray(tris); rays = np.ascontiguousarray(rays)
+        out = np.empty((rays.shape[0], max_steps), dtype=np.int16)
+        dll().og_traverse_record(self.ptr, tris.ctypes.data, rays.ctypes.data, out.ctypes.data, max_steps, rays.shape[0])
+        return out
+
+    def record_cells(self, tris: np.ndarray, rays: np.ndarray, max_steps: int = 128) -> np.ndarray:
+        """Statistics: (num_rays, max_steps) int32, index of each visited cell, -1 padded."""
+        tris = np.ascontiguousarray(tris); rays = np.ascontiguousarray(rays)
+        out = np.empty((rays.shape[0], max_steps), dtype=np.int32)
+        dll().og_traverse_record_cells(self.ptr, tris.ctypes.data, rays.ctypes.data, out.ctypes.data, max_steps, rays.shape[0])
+        return out
