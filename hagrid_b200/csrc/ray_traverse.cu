@@ -6,18 +6,18 @@
 // shrinking tmax, and the ray stops when `hit.t <= texit` or the voxel leaves
 // the grid. What is different is how rays are mapped onto the machine:
 //
-//   * persistent warps (one resident grid sized to the SM count) pull rays
-//     from a global counter, so a lane whose ray ends is refilled instead of
-//     idling until the slowest ray of its warp finishes;
-//   * the cell walk and the ray/triangle tests are two separate warp phases.
-//     Lanes that reach a non-empty cell park their reference range; the warp
-//     keeps stepping the other lanes through (mostly empty) cells and only
-//     then runs the triangle phase with most lanes busy, one triangle per lane
-//     per iteration, until too few lanes have work left (`__ballot_sync`
-//     population counts drive the phase changes).
+//   * coherent buffers (a W x H raster of camera rays, recognised on the device or on the host): a warp
+//     traces an 8x4 pixel tile instead of a 32x1 strip, and resident warps pull tiles from a global
+//     counter (kernel A2) so that no warp slot idles behind the slowest warp of its block;
+//   * incoherent buffers: persistent warps whose lanes are refilled from a ray counter as their rays
+//     end; each iteration the warp serves the larger of two groups of lanes, those that need a cell
+//     step and those that own references to test (kernel B, `__ballot_sync` population counts);
+//   * host-buffer frames are cut into chunks whose upload, traversal and download overlap.
 //
-// The grid, the references and the triangles (tens of MB) live in the 126 MB
-// L2; compulsory HBM traffic is 32 B/ray in + 16 B/hit out.
+// ncu (profiles/): both kernels issue at 72-78 % of the SM's peak rate; the coherent kernel is bound by
+// instruction issue (2 090 warp instructions per 32 rays at 23 of 32 lanes active), the incoherent
+// one by the latency of its dependent L2 loads. The grid, the references and the triangles (tens of
+// MB) live in the 126 MB L2; compulsory HBM traffic is 32 B/ray in + 16 B/hit out.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -334,47 +334,17 @@ __device__ __forceinline__ void trace_one(const TraversalParams& P, const uint32
 }
 
 constexpr int kTileBlock = 128;
+constexpr int kTileBlocksPerSm = 10;     // <= 51 registers: 40 resident warps per SM, measured best of 8 / 10 / 12
 
-/// ptxas re-loads kernel parameters from the constant bank inside the hot loops (about one issue slot in
-/// ten) instead of keeping them in registers; it sees through arithmetic identities and through shuffles
-/// of uniform values. A volatile shared-memory load is executed exactly once, so a parameter that took
-/// the detour through shared memory has to stay in a register.
-/// kHoist: 0 = leave it to ptxas, 1 = pointers and integers, 2 = the float constants too.
-struct HoistBox {
-    unsigned long long ptr[4];
-    int   i[6];
-    float f[9];
-};
-
-template <typename CellT, bool kPrimId, int kMinBlocks, int kHoist>
-__global__ void __launch_bounds__(kTileBlock, kMinBlocks)
-traverse_tiles(const __grid_constant__ TraversalParams P0,
+template <typename CellT, bool kPrimId>
+__global__ void __launch_bounds__(kTileBlock, kTileBlocksPerSm)
+traverse_tiles(const __grid_constant__ TraversalParams P,
                const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
                const int* __restrict__ layout, int host_width, int* __restrict__ next_tile) {
     constexpr unsigned kAll = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    TraversalParams P = P0;
-    if (kHoist >= 1) {
-        __shared__ HoistBox box;
-        if (threadIdx.x == 0) {
-            box.ptr[0] = reinterpret_cast<unsigned long long>(entries); box.ptr[1] = reinterpret_cast<unsigned long long>(cells);
-            box.ptr[2] = reinterpret_cast<unsigned long long>(ref_ids); box.ptr[3] = reinterpret_cast<unsigned long long>(tris);
-            box.i[0] = P.dims_x; box.i[1] = P.dims_y; box.i[2] = P.dims_z; box.i[3] = P.top_x; box.i[4] = P.top_y; box.i[5] = P.shift;
-            box.f[0] = P.min_x; box.f[1] = P.min_y; box.f[2] = P.min_z; box.f[3] = P.cell_x; box.f[4] = P.cell_y; box.f[5] = P.cell_z;
-            box.f[6] = P.inv_x; box.f[7] = P.inv_y; box.f[8] = P.inv_z;
-        }
-        __syncthreads();
-        const volatile HoistBox& vb = box;
-        entries = reinterpret_cast<const uint32_t*>(vb.ptr[0]); cells = reinterpret_cast<const CellT*>(vb.ptr[1]);
-        ref_ids = reinterpret_cast<const int*>(vb.ptr[2]); tris = reinterpret_cast<const Tri*>(vb.ptr[3]);
-        P.dims_x = vb.i[0]; P.dims_y = vb.i[1]; P.dims_z = vb.i[2]; P.top_x = vb.i[3]; P.top_y = vb.i[4]; P.shift = vb.i[5];
-        if (kHoist >= 2) {
-            P.min_x = vb.f[0]; P.min_y = vb.f[1]; P.min_z = vb.f[2]; P.cell_x = vb.f[3]; P.cell_y = vb.f[4]; P.cell_z = vb.f[5];
-            P.inv_x = vb.f[6]; P.inv_y = vb.f[7]; P.inv_z = vb.f[8];
-        }
-    }
     const int width = layout ? __ldg(layout) : host_width;
     const int num_tiles = (num_rays + 31) >> 5;
     const int first_dynamic = gridDim.x * (kTileBlock / 32);
@@ -391,20 +361,31 @@ traverse_tiles(const __grid_constant__ TraversalParams P0,
     }
 }
 
-// ---------------------------------------------------------------------------
-// Kernel B: persistent warps, phase-scheduled (incoherent buffers).
-// ---------------------------------------------------------------------------
 constexpr int kBlockThreads = 128;
-constexpr int kTriPhaseMinLanes = 12;   // leave the triangle phase when fewer lanes have work
-constexpr int kRefillMinLanes   = 8;    // fetch new rays when at least this many lanes are idle
+
+// ---------------------------------------------------------------------------
+// Kernel B: persistent warps with majority scheduling (incoherent buffers). Every iteration the warp
+// counts the lanes that need a cell step and the lanes that own references and serves the larger
+// group (tools/warp_sim.py, policy "count": 0.31 cell + 0.34 triangle iterations per ray against
+// 0.86 + 0.29 when the cell phase runs until every lane owns references). With fewer instructions the
+// kernel is bound by the latency of its dependent loads, the ray-counter atomic first among them (ncu:
+// 13 % of the stall samples), so rays are reserved 32 at a time two blocks ahead: the atomic of a block
+// is issued one block before its value is read. Software prefetches of the next voxel-map word and of
+// the next triangle were measured and lose (the L1 tag stage is the second bottleneck), and so does a
+// per-reference copy of the triangles (64-byte records: one latency less per test, but the duplicates
+// of a triangle no longer share cache lines).
+// ---------------------------------------------------------------------------
+constexpr int kVoteBlock = 32;          // rays reserved per atomic
+constexpr int kVoteRefillMinLanes = 4;
+constexpr int kVoteBlocksPerSm = 10;    // <= 51 registers
 
 template <typename CellT, bool kPrimId>
-__global__ void __launch_bounds__(kBlockThreads)
-traverse_persistent(const __grid_constant__ TraversalParams P,
-                    const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
-                    const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
-                    const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
-                    int* __restrict__ next_ray) {
+__global__ void __launch_bounds__(kBlockThreads, kVoteBlocksPerSm)
+traverse_voting(const __grid_constant__ TraversalParams P,
+                const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
+                const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
+                const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
+                int* __restrict__ next_ray) {
     constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
     constexpr unsigned kAll = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -414,28 +395,43 @@ traverse_persistent(const __grid_constant__ TraversalParams P,
     int   ref = -1;             // reference being tested next (-1: none parked)
     int   cur = 0, end = 0;     // rest of the parked reference range
     float texit = 0.0f;
-    bool  drained = false;      // the global ray counter ran out
+
+    // ray reservation: [pool, pool_end) is handed out now, `ahead` is the block after it, `requested`
+    // (lane 0) is the atomic in flight for the block after that: its value is read one block later
+    int pool, pool_end, ahead, requested = 0;
+    {
+        int first = 0;
+        if (lane == 0) first = atomicAdd(next_ray, 2 * kVoteBlock);
+        first = __shfl_sync(kAll, first, 0);
+        pool = min(first, num_rays); pool_end = min(first + kVoteBlock, num_rays);
+        ahead = first + kVoteBlock;
+        if (lane == 0) requested = atomicAdd(next_ray, kVoteBlock);
+    }
 
     while (true) {
-        // ---- refill idle lanes from the global counter
+        // ---- refill idle lanes from the reserved block
         const unsigned idle = __ballot_sync(kAll, ray_id < 0);
+        const bool drained = pool >= num_rays;
         if (idle == kAll && drained) break;
-        if (!drained && __popc(idle) >= kRefillMinLanes) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(next_ray, __popc(idle));
-            base = __shfl_sync(kAll, base, 0);
-            if (base >= num_rays) drained = true;
+        if (!drained && __popc(idle) >= kVoteRefillMinLanes) {
             if (ray_id < 0) {
-                const int id = base + __popc(idle & ((1u << lane) - 1u));
-                if (id < num_rays) {
+                const int id = pool + __popc(idle & ((1u << lane) - 1u));
+                if (id < pool_end) {
                     if (start_ray(r, P, rays, id)) ray_id = id;
                     else finish_ray<kPrimId>(r, hits, id);
                 }
             }
+            pool = min(pool + __popc(idle), pool_end);
+            if (pool == pool_end) {            // block used up: move on to the next one, ask for another
+                pool = min(ahead, num_rays); pool_end = min(ahead + kVoteBlock, num_rays);
+                ahead = __shfl_sync(kAll, requested, 0);
+                if (lane == 0) requested = atomicAdd(next_ray, kVoteBlock);
+            }
         }
 
-        // ---- cell phase: every lane without parked references walks on
-        while (__any_sync(kAll, ray_id >= 0 && ref < 0)) {
+        const unsigned walkers = __ballot_sync(kAll, ray_id >= 0 && ref < 0);
+        const unsigned testers = __ballot_sync(kAll, ref >= 0);
+        if (__popc(walkers) >= __popc(testers)) {
             if (ray_id >= 0 && ref < 0) {
                 dev::CellBox cell;
                 texit = enter_cell(r, P, entries, cells, cell);
@@ -453,24 +449,16 @@ traverse_persistent(const __grid_constant__ TraversalParams P,
                     ray_id = -1;
                 }
             }
-        }
-
-        // ---- triangle phase: one triangle per busy lane per iteration
-        unsigned busy = __ballot_sync(kAll, ref >= 0);
-        while (busy) {
-            if (ref >= 0) {
-                int next;
-                if (kSentinel) { next = __ldg(ref_ids + cur++); r.steps++; }
-                else           { next = cur < end ? __ldg(ref_ids + cur++) : -1; }
-                intersect_tri(r, tris, ref);
-                ref = next;
-                if (ref < 0 && (r.hit_t <= texit || outside(r, P))) {
-                    finish_ray<kPrimId>(r, hits, ray_id);
-                    ray_id = -1;
-                }
+        } else if (ref >= 0) {
+            int next;
+            if (kSentinel) { next = __ldg(ref_ids + cur++); r.steps++; }
+            else           { next = cur < end ? __ldg(ref_ids + cur++) : -1; }
+            intersect_tri(r, tris, ref);
+            ref = next;
+            if (ref < 0 && (r.hit_t <= texit || outside(r, P))) {
+                finish_ray<kPrimId>(r, hits, ray_id);
+                ray_id = -1;
             }
-            busy = __ballot_sync(kAll, ref >= 0);
-            if (__popc(busy) < kTriPhaseMinLanes) break;
         }
     }
 }
@@ -524,8 +512,9 @@ void prepare_streams(DeviceState& st) {
     HGB_CUDA(cudaMalloc(&st.stream_counters, 64));
 }
 
-// 0: per thread, buffer order   1: persistent   2: per thread, re-tiled when a raster is detected
-// 3 (default): 2 for buffers that are (or may be) rasters, 1 once a buffer is known not to be one
+// 0: per thread, buffer order   1: persistent warps, majority-scheduled   2: per thread, re-tiled when a raster is detected
+// 4: resident warps pulling tiles, re-tiled when a raster is detected
+// 3 (default): 4 for buffers that are (or may be) rasters, 1 once a buffer is known not to be one
 int g_variant = -1;
 
 // Host-buffer frames: rays per full-size chunk (tuned on B200/PCIe 5: ~350 K rays = 11 MB up, 5.6 MB down)
@@ -539,37 +528,23 @@ int traverse_variant() {
     return g_variant;
 }
 
-/// Enqueues one traversal launch on `stream`. variant 1 = persistent (needs `counter`), otherwise one
-/// thread per ray, re-tiled by the raster width in `layout[0]` (device) or `host_width`.
+/// Enqueues one traversal launch on `stream`: 1 = persistent voting warps, 4 = resident warps pulling tiles
+/// (both need `counter`), otherwise one thread per ray; 2 and 4 re-tile by the raster width in
+/// `layout[0]` (device) or `host_width`.
 template <typename CellT, bool kPrimId>
 void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays,
              int variant, const int* layout, int host_width, int* counter, int num_sms, cudaStream_t stream) {
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
-    if (variant >= 4) {
-        // tile-pulling resident warps; experiment matrix: registers allowed x parameter hoisting
-        //   4: 12 blocks/SM (<=40 regs)   5: 10 (<=51)   6: 8 (<=64)          ... ptxas places the constants
-        //   7: 10 blocks/SM, pointers+ints hoisted   8: 8 blocks/SM, pointers+ints   9: 8 blocks/SM, everything
+    if (variant == 4) {
         HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
-        static const int kPerSm[] = {12, 10, 8, 10, 8, 8};
-        const int blocks = min(num_sms * kPerSm[min(variant, 9) - 4], round_div(num_rays, kTileBlock));
-#define HGB_TILES(MINB, HOIST) traverse_tiles<CellT, kPrimId, MINB, HOIST><<<blocks, kTileBlock, 0, stream>>>( \
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, counter)
-        switch (variant) {
-            case 4: HGB_TILES(12, 0); break;
-            case 5: HGB_TILES(10, 0); break;
-            case 6: HGB_TILES(8, 0); break;
-            case 7: HGB_TILES(10, 1); break;
-            case 8: HGB_TILES(8, 1); break;
-            default: HGB_TILES(8, 2); break;
-        }
-#undef HGB_TILES
-        count_launch();
+        const int blocks = min(num_sms * kTileBlocksPerSm, round_div(num_rays, kTileBlock));
+        traverse_tiles<CellT, kPrimId><<<blocks, kTileBlock, 0, stream>>>(
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, counter); count_launch();
     } else if (variant == 1) {
-        static int occ = 0;
-        if (!occ) HGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traverse_persistent<CellT, kPrimId>, kBlockThreads, 0));
         HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
-        const int blocks = min(num_sms * max(occ, 1), round_div(num_rays, kBlockThreads));
-        traverse_persistent<CellT, kPrimId><<<blocks, kBlockThreads, 0, stream>>>(
+        // every warp reserves two blocks of rays up front: no more warps than there are blocks
+        const int blocks = max(1, min(num_sms * kVoteBlocksPerSm, round_div(num_rays, 2 * kVoteBlock * (kBlockThreads / 32))));
+        traverse_voting<CellT, kPrimId><<<blocks, kBlockThreads, 0, stream>>>(
             g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, counter); count_launch();
     } else {
         traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128, 0, stream>>>(
@@ -601,7 +576,7 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
     require_setup(grid);
     DeviceState& st = device_state();
     int variant = traverse_variant();
-    if (variant >= 2) {
+    if (variant >= 2 && variant <= 4) {
         if (rays != st.seen_rays || num_rays != st.seen_count) {
             // new buffer: look at its layout on the device, asynchronously; this launch
             // reads the answer from device memory, later launches also know it on the host
@@ -612,9 +587,9 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
             st.seen_rays = rays;
             st.seen_count = num_rays;
         }
-        if (variant == 3) variant = *static_cast<volatile int*>(st.layout_host) == 0 ? 1 : 2;
+        if (variant == 3) variant = *static_cast<volatile int*>(st.layout_host) == 0 ? 1 : 4;
     }
-    enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, variant >= 2 ? st.layout : nullptr, 0,
+    enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, (variant == 2 || variant == 4) ? st.layout : nullptr, 0,
                             st.counter, st.num_sms, 0);
     HGB_CUDA(cudaGetLastError());
 }
@@ -669,9 +644,9 @@ void launch_host_frame(const Grid& grid, const CellT* cells, const Tri* tris, co
 
     int variant = traverse_variant();
     int width = 0;
-    if (variant >= 2) {
+    if (variant >= 2 && variant <= 4) {
         width = host_raster_width(host_rays, num_rays);
-        variant = width > 0 ? 2 : (variant == 3 ? 1 : 0);
+        variant = width > 0 ? (variant == 2 ? 2 : 4) : (variant == 3 ? 1 : 0);
     }
     // Chunks are whole 4-row tile bands of a raster, else whole blocks. Full-size chunks keep the copy
     // engines busy with few, large transfers; the last one is split 1/2, 1/4, 1/4 because nothing

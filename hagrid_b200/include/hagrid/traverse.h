@@ -26,8 +26,9 @@ void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, 
 void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays, Hit* host_hits, int num_rays,
                         Ray* dev_rays, Hit* dev_hits, bool prim_ids);
 
-/// Tuning switches ("traverse_variant": 0 = one thread per ray, 1 = persistent
-/// phase-scheduled warps). Returns false for unknown keys.
+/// Tuning switches: "traverse_variant" (0 = one thread per ray, 1 = persistent phase-scheduled warps,
+/// 2 = one thread per ray re-tiled 8x4 on rasters, 4 = resident warps pulling 8x4 tiles, 3 = automatic) and
+/// "host_frame_chunk_rays" (chunk size of traverse_grid_host). Returns false for unknown keys.
 bool set_traversal_option(const char* key, int value);
 
 } // namespace hagrid

@@ -77,7 +77,10 @@ HGB_API const char* hgb_last_error(void);
 HGB_API int  hgb_device_count(void);
 /* Tuning/diagnostic switches of this library (no reference counterpart; the
  * reference build of this ABI accepts and ignores them). Keys:
- *   "traverse_variant"  0 = one thread per ray, 1 = persistent phase-scheduled (default)
+ *   "traverse_variant"       0 = one thread per ray, 1 = persistent phase-scheduled warps, 2 = one thread per
+ *                            ray re-tiled 8x4 when the buffer is a raster, 4 = resident warps pulling 8x4 tiles,
+ *                            3 = automatic (default: 4 for rasters, 1 otherwise)
+ *   "host_frame_chunk_rays"  rays per full-size chunk of hgb_traverse_grid_host's pipeline
  * Returns 0 when the key is known. */
 HGB_API int  hgb_set_option(const char* key, int value);
 

@@ -33,7 +33,7 @@ def test_front_end_links_against_this_library():
                  "hagrid::compress_grid(", "hagrid::setup_traversal(", "hagrid::traverse_grid(", "hagrid::profile(",
                  "hagrid::MemManager::alloc_slot("):
         assert name in syms, name
-    assert "traverse_persistent" in syms          # our kernels, not the reference's `traverse<...>`
+    assert "traverse_voting" in syms and "traverse_tiles" in syms          # our kernels, not the reference's `traverse<...>`
 
 
 def _report(text):

@@ -13,7 +13,7 @@ from util import FIXTURES, STAGES, Golden, grid_diff, t_close
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = (0, 1, 2, 3)    # per-thread / persistent / per-thread re-tiled / automatic
+VARIANTS = (0, 1, 2, 3, 4)    # per-thread / persistent / per-thread re-tiled / automatic / tile-pulling resident warps
 
 
 def run_stage(sc, stage, g):
