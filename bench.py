@@ -141,6 +141,13 @@ def main():
     ref_lib_path = ROOT / "oracle" / "_ref" / "libhagrid_ref.so"
     if reference and not ref_lib_path.exists():
         return reference_on_cpu(args, rank)
+    launched_ranks = world
+    if reference:
+        # cg-saarland/hagrid is a single-process, single-GPU program (SURVEY.md quick facts): its arm runs
+        # on rank 0's GPU alone, whatever N was launched; the other ranks leave without work
+        if rank != 0:
+            return
+        world = 1
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hagrid_b200 path has no CPU fallback")
@@ -245,7 +252,7 @@ def main():
             pass
         line = {
             "metric": "Mrays/s, primary rays (closest hit, bit-exact prim ids)", "value": round(value, 1), "unit": "Mrays/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 5),
+            "n_gpus": launched_ranks, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 5),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": args.impl,
             "config": {"workload": "C2: sponza262k stand-in (262267 tris), 1920x1080 primary rays, -td 0.15 -sd 3.0 -a 0.995 -e 3",
@@ -269,6 +276,7 @@ def main():
         }
         line.update(inc)
         if reference:
+            line["ranks_used"] = 1
             line["cpu_baseline"] = {"value": line["value"], "unit": "Mrays/s", "cores": 1, "kind": "reference",
                                     "sample": "whole workload; cg-saarland/hagrid has no CPU build/traverse path, so the arm runs its "
                                               "CUDA sources rebuilt for sm_100a (oracle/_ref) on the same GPU, one host thread"}

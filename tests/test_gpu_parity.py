@@ -215,6 +215,51 @@ def test_c3_compressed_grid_gives_same_hits(lib, sponza):
     sc2.close()
 
 
+def _same_grid_as_reference(lib, ref_lib, tris, td, sd, compress=False):
+    a, b = Scene(tris, keep_alive=True, lib=ref_lib), Scene(tris, keep_alive=True, lib=lib)
+    a.build_all(td, sd, 0.995, 3, compress); b.build_all(td, sd, 0.995, 3, compress)
+    ia, aa = dump(a); ib, ab = dump(b)
+    assert grid_diff(ib, ab, (ia,) + aa) == []
+    return a, b, ia
+
+
+def test_c4_two_million_triangle_hairball_matches_reference(lib, ref_lib):
+    """BASELINE.json C4 at full size: the complete construction pipeline, byte for byte."""
+    a, b, info = _same_grid_as_reference(lib, ref_lib, scenes.hairball(), 0.12, 2.4)
+    assert info["num_refs"] > 10_000_000 and info["num_cells"] > 1_000_000
+    a.close(); b.close()
+
+
+def test_c5_san_miguel_scale_primary_and_bounce_rays_sharded_over_8_ranks(lib, ref_lib):
+    """BASELINE.json C5 at full size (7.8 M triangles, 1920x1080 primary + one bounce): same grid and same
+    hits as the reference; tracing the 8 rank shards of hagrid_b200.sharding separately gives the unsharded result."""
+    from hagrid_b200 import sharding
+    tris = scenes.sanmiguel7p8m()
+    a, b, info = _same_grid_as_reference(lib, ref_lib, tris, 0.15, 3.0)
+    assert 0 < info["num_refs"] < 2**31 and info["num_entries"] < 2**30      # int32 counts, Entry.begin is 30 bits
+    primary = scenes.default_view(tris)
+    b.setup_traversal()
+    first = b.trace(primary, HIT_PRIM_ID)
+    bounce = scenes.bounce_rays(tris, primary, first["id"], first["t"])
+    second = b.trace(bounce, HIT_PRIM_ID)
+    a.setup_traversal()
+    for rays, got in ((primary, first), (bounce, second)):
+        want = a.trace(rays, HIT_PRIM_ID)
+        assert np.array_equal(got["id"], want["id"]) and np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    b.setup_traversal()
+    world = 8
+    for rays, whole in ((primary, first), (bounce, second)):
+        parts = []
+        for rank in range(world):
+            lo, hi = sharding.shard_bounds(rays.shape[0], rank, world, sharding.raster_granule(1920))
+            parts.append(b.trace(rays[lo:hi], HIT_PRIM_ID))
+        joined = np.concatenate(parts)
+        assert np.array_equal(joined["id"], whole["id"]) and np.array_equal(joined["t"].view(np.uint32), whole["t"].view(np.uint32))
+    hit = first["id"] >= 0
+    assert hit.mean() > 0.5 and (second["t"][second["id"] >= 0] > 0).all()
+    a.close(); b.close()
+
+
 def test_build_is_deterministic(lib):
     tris = scenes.hairball(60000, seed=2)
     a, b = Scene(tris, lib=lib), Scene(tris, keep_alive=True, lib=lib)
