@@ -217,6 +217,27 @@ def main():
         e2e_ms.append(a.elapsed_time(b))
     e2e_ok = bool(np.array_equal(h_hits.numpy().view(np.int32)[:, 0], hits["id"]))
 
+    # ---- secondary number: one viewer frame (camera -> BGRA image in host memory), src/main.cpp:598-621
+    frame = {}
+    if rank == 0:
+        from hagrid_b200 import make_camera
+        lo_, hi_ = scenes.scene_bbox(tris)
+        eye_ = 0.5 * (lo_ + hi_)
+        cam = make_camera(eye_, eye_ + np.array([0, 0, 1], np.float32), (0, 1, 0), 60.0, WIDTH / HEIGHT, lib=lib)
+        clip = float(np.linalg.norm(hi_ - lo_))
+        image = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory()
+        render = lambda: lib.check(lib.dll.hgb_render_frame(scene._h, cam.ctypes.data, clip, WIDTH, HEIGHT, 0, image.data_ptr()), "frame")
+        for _ in range(2):
+            render()
+        t0 = time.perf_counter()
+        reps = 5 if reference else 20
+        for _ in range(reps):
+            render()
+        frame = {"viewer_frame_ms": round((time.perf_counter() - t0) * 1e3 / reps, 3),
+                 "viewer_frame": "hgb_render_frame, 1920x1080 depth image to pinned host memory, wall clock; " +
+                                 ("reference: CPU gen_rays + upload + traverse_grid + download + CPU update_surface" if reference
+                                  else "one fused launch (generate, trace, colour) + 4 B/pixel download")}
+
     # ---- secondary numbers: incoherent rays on the compressed grid (C3)
     inc = {}
     if rank == 0 and not os.environ.get("HGB_BENCH_SKIP_C3"):
@@ -275,6 +296,7 @@ def main():
             "hit_fraction": round(float((hits["id"] >= 0).mean()), 4),
         }
         line.update(inc)
+        line.update(frame)
         if reference:
             line["ranks_used"] = 1
             line["cpu_baseline"] = {"value": line["value"], "unit": "Mrays/s", "cores": 1, "kind": "reference",

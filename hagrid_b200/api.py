@@ -70,6 +70,9 @@ _SIGNATURES = {
     "hgb_traverse_timed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p]),
     "hgb_traverse_grid_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "hgb_make_camera": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
+    "hgb_generate_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]),
+    "hgb_render_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hgb_grid_get_info": (C.c_int, [C.c_void_p, C.POINTER(GridInfo)]),
     "hgb_grid_download": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "hgb_grid_upload": (C.c_int, [C.c_void_p, C.POINTER(GridInfo), C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -120,6 +123,15 @@ class Library:
 
     def synchronize(self):
         self.check(self.dll.hgb_device_synchronize(), "synchronize")
+
+
+def make_camera(eye, center, up, fov: float, ratio: float, lib: "Library | None" = None) -> np.ndarray:
+    """gen_camera (src/main.cpp:42-50): 12 floats eye, right, up, dir."""
+    lib = lib or library()
+    e, c, u = (np.ascontiguousarray(v, dtype="<f4") for v in (eye, center, up))
+    cam = np.empty(12, dtype="<f4")
+    lib.check(lib.dll.hgb_make_camera(_ptr(e), _ptr(c), _ptr(u), fov, ratio, _ptr(cam)), "make_camera")
+    return cam
 
 
 _default_library: Library | None = None
@@ -219,6 +231,26 @@ class Scene:
         self.lib.check(self.lib.dll.hgb_traverse_grid_host(self._h, _ptr(rays), _ptr(hits), rays.shape[0], hit_mode),
                        "traverse_grid_host")
         return hits
+
+    # --- camera frames (src/main.cpp:42-111, 591-625) ------------------------------
+    def generate_rays(self, cam: np.ndarray, clip: float, width: int, height: int) -> np.ndarray:
+        """gen_rays on the device, downloaded: (width*height,) rays in scan-line order."""
+        cam = np.ascontiguousarray(cam, dtype="<f4")
+        n = width * height
+        d_rays = self.device_alloc(n * 32)
+        try:
+            self.lib.check(self.lib.dll.hgb_generate_rays(self._h, _ptr(cam), clip, width, height, d_rays), "generate_rays")
+            return self.to_host(np.empty(n, dtype=RAY_DTYPE), d_rays)
+        finally:
+            self.device_free(d_rays)
+
+    def render_frame(self, cam: np.ndarray, clip: float, width: int, height: int, mode: int, out: np.ndarray | None = None):
+        """One viewer frame: (height, width, 4) BGRA bytes."""
+        cam = np.ascontiguousarray(cam, dtype="<f4")
+        if out is None:
+            out = np.empty((height, width, 4), dtype=np.uint8)
+        self.lib.check(self.lib.dll.hgb_render_frame(self._h, _ptr(cam), clip, width, height, mode, _ptr(out)), "render_frame")
+        return out
 
     # --- grid inspection / transplant -------------------------------------------
     def info(self) -> GridInfo:

@@ -22,6 +22,13 @@
 
 #include "hagrid_b200.h"
 
+#ifdef HGB_REFERENCE_BUILD
+// The reference's own gen_camera / gen_rays / update_surface (oracle/ref_frontend.cpp includes src/main.cpp)
+extern "C" void hgb_ref_gen_camera(const float* eye, const float* center, const float* up, float fov, float ratio, float* cam12);
+extern "C" const void* hgb_ref_gen_rays(const float* cam12, float clip, int w, int h);
+extern "C" void hgb_ref_update_surface(int mode, const void* hits, float clip, int w, int h, void* bgra);
+#endif
+
 namespace hagrid {
 #ifdef HGB_REFERENCE_BUILD
 // Second build of the reference's traverse.cu with the `hit.id = steps` line
@@ -49,11 +56,13 @@ struct hgb_scene {
     Ray* frame_rays;
     Hit* frame_hits;
     int frame_capacity;
+    unsigned* frame_pixels;
+    int pixel_capacity;
     unsigned long long grid_epoch;      // bumped by everything that changes the grid
 
     hgb_scene(int dev, bool keep)
         : mem(keep), tris(nullptr), num_tris(0), device(dev),
-          frame_rays(nullptr), frame_hits(nullptr), frame_capacity(0), grid_epoch(0)
+          frame_rays(nullptr), frame_hits(nullptr), frame_capacity(0), frame_pixels(nullptr), pixel_capacity(0), grid_epoch(0)
     {
         grid.entries = nullptr;
         grid.ref_ids = nullptr;
@@ -102,6 +111,16 @@ static void release_grid(hgb_scene* s) {
 static struct { const hgb_scene* scene; unsigned long long epoch; } g_setup = {nullptr, 0};
 
 static bool setup_matches(const hgb_scene* s) { return g_setup.scene == s && g_setup.epoch == s->grid_epoch; }
+
+/// Device staging buffers of a host-buffer frame, from the scene's pool
+static void reserve_frame(hgb_scene* s, int num_rays) {
+    if (num_rays <= s->frame_capacity) return;
+    s->mem.free(s->frame_rays);
+    s->mem.free(s->frame_hits);
+    s->frame_rays = s->mem.alloc<Ray>(num_rays);
+    s->frame_hits = s->mem.alloc<Hit>(num_rays);
+    s->frame_capacity = num_rays;
+}
 
 static void run_traverse(hgb_scene* s, const Ray* rays, Hit* hits, int n, int hit_mode) {
     if (hit_mode == HGB_HIT_PRIM_ID) {
@@ -161,6 +180,7 @@ void hgb_scene_destroy(hgb_scene* s) {
         s->mem.free(s->tris);
         s->mem.free(s->frame_rays);
         s->mem.free(s->frame_hits);
+        s->mem.free(s->frame_pixels);
     }
     delete s;
 }
@@ -278,13 +298,7 @@ int hgb_traverse_grid_host(hgb_scene* s, const void* host_rays, void* host_hits,
     if (!s->grid.entries) return fail("traverse_grid_host: no grid");
     if (!setup_matches(s)) return fail("traverse_grid_host: hgb_setup_traversal was not called for this grid");
     if (num_rays <= 0) return 0;
-    if (num_rays > s->frame_capacity) {
-        s->mem.free(s->frame_rays);
-        s->mem.free(s->frame_hits);
-        s->frame_rays = s->mem.alloc<Ray>(num_rays);
-        s->frame_hits = s->mem.alloc<Hit>(num_rays);
-        s->frame_capacity = num_rays;
-    }
+    reserve_frame(s, num_rays);
 #ifdef HGB_REFERENCE_BUILD
     // the reference's frame, verbatim: blocking upload, launch, blocking download (src/main.cpp:599-613)
     s->mem.copy<Copy::HST_TO_DEV>(s->frame_rays, static_cast<const Ray*>(host_rays), num_rays);
@@ -293,6 +307,70 @@ int hgb_traverse_grid_host(hgb_scene* s, const void* host_rays, void* host_hits,
 #else
     traverse_grid_host(s->grid, s->tris, static_cast<const Ray*>(host_rays), static_cast<Hit*>(host_hits), num_rays,
                        s->frame_rays, s->frame_hits, hit_mode == HGB_HIT_PRIM_ID);
+#endif
+    return 0;
+}
+
+int hgb_make_camera(const float eye[3], const float center[3], const float up[3], float fov, float ratio, float cam_out[12]) {
+    if (!eye || !center || !up || !cam_out) return fail("make_camera: null argument");
+#ifdef HGB_REFERENCE_BUILD
+    hgb_ref_gen_camera(eye, center, up, fov, ratio, cam_out);
+#else
+    const FrameCamera cam = make_camera(vec3(eye[0], eye[1], eye[2]), vec3(center[0], center[1], center[2]),
+                                        vec3(up[0], up[1], up[2]), fov, ratio);
+    const vec3 v[4] = {cam.eye, cam.right, cam.up, cam.dir};
+    for (int i = 0; i < 4; i++) { cam_out[3 * i] = v[i].x; cam_out[3 * i + 1] = v[i].y; cam_out[3 * i + 2] = v[i].z; }
+#endif
+    return 0;
+}
+
+#ifndef HGB_REFERENCE_BUILD
+static FrameCamera camera_of(const float* c) {
+    FrameCamera cam;
+    cam.eye = vec3(c[0], c[1], c[2]); cam.right = vec3(c[3], c[4], c[5]);
+    cam.up = vec3(c[6], c[7], c[8]); cam.dir = vec3(c[9], c[10], c[11]);
+    return cam;
+}
+#endif
+
+int hgb_generate_rays(hgb_scene* s, const float cam[12], float clip, int width, int height, void* dev_rays) {
+    if (!bind(s)) return -1;
+    if (!cam || !dev_rays || width <= 0 || height <= 0) return fail("generate_rays: bad argument");
+#ifdef HGB_REFERENCE_BUILD
+    // the reference generates on the host and uploads (src/main.cpp:598-599)
+    const Ray* host = static_cast<const Ray*>(hgb_ref_gen_rays(cam, clip, width, height));
+    s->mem.copy<Copy::HST_TO_DEV>(static_cast<Ray*>(dev_rays), host, size_t(width) * height);
+#else
+    generate_rays(camera_of(cam), clip, width, height, static_cast<Ray*>(dev_rays));
+#endif
+    return 0;
+}
+
+int hgb_render_frame(hgb_scene* s, const float cam[12], float clip, int width, int height, int display_mode, void* host_bgra) {
+    if (!bind(s)) return -1;
+    if (!s->grid.entries) return fail("render_frame: no grid");
+    if (!setup_matches(s)) return fail("render_frame: hgb_setup_traversal was not called for this grid");
+    if (!cam || !host_bgra || width <= 0 || height <= 0) return fail("render_frame: bad argument");
+    if (display_mode < 0 || display_mode > 2) return fail("render_frame: display_mode must be 0, 1 or 2");
+    const int n = width * height;
+#ifdef HGB_REFERENCE_BUILD
+    // one iteration of the reference's viewer loop, with its own functions (src/main.cpp:598-621)
+    static std::vector<Hit> host_hits;
+    host_hits.resize(n);
+    reserve_frame(s, n);
+    const Ray* host_rays = static_cast<const Ray*>(hgb_ref_gen_rays(cam, clip, width, height));
+    s->mem.copy<Copy::HST_TO_DEV>(s->frame_rays, host_rays, n);
+    traverse_grid(s->grid, s->tris, s->frame_rays, s->frame_hits, n);
+    s->mem.copy<Copy::DEV_TO_HST>(host_hits.data(), s->frame_hits, n);
+    hgb_ref_update_surface(display_mode, host_hits.data(), clip, width, height, host_bgra);
+#else
+    if (n > s->pixel_capacity) {
+        s->mem.free(s->frame_pixels);
+        s->frame_pixels = s->mem.alloc<unsigned>(n);
+        s->pixel_capacity = n;
+    }
+    render_frame(s->grid, s->tris, camera_of(cam), clip, width, height, display_mode, s->frame_pixels);
+    s->mem.copy<Copy::DEV_TO_HST>(static_cast<unsigned*>(host_bgra), s->frame_pixels, n);
 #endif
     return 0;
 }

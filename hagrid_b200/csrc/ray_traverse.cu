@@ -92,10 +92,8 @@ __device__ __forceinline__ void intersect_tri(RayState& r, const Tri* __restrict
 
 /// Loads ray `id`, clips it against the grid box and finds its first voxel
 /// (src/traverse.cu:36-54). Returns false when the ray misses the grid.
-__device__ __forceinline__ bool start_ray(RayState& r, const TraversalParams& P, const Ray* __restrict__ rays, int id) {
+__device__ __forceinline__ bool init_ray(RayState& r, const TraversalParams& P, const float4 a, const float4 b) {
     using namespace dev;
-    const float4 a = ldg4_stream(reinterpret_cast<const float4*>(rays + id) + 0);
-    const float4 b = ldg4_stream(reinterpret_cast<const float4*>(rays + id) + 1);
     r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tmin = a.w;
     r.dx = b.x; r.dy = b.y; r.dz = b.z;
     r.ix = safe_rcp(b.x); r.iy = safe_rcp(b.y); r.iz = safe_rcp(b.z);
@@ -117,6 +115,12 @@ __device__ __forceinline__ bool start_ray(RayState& r, const TraversalParams& P,
     r.vy = min(P.dims_y - 1, max(0, trunc_to_int(mul(sub(fma(r.dy, tstart, r.oy), P.min_y), P.inv_y))));
     r.vz = min(P.dims_z - 1, max(0, trunc_to_int(mul(sub(fma(r.dz, tstart, r.oz), P.min_z), P.inv_z))));
     return true;
+}
+
+__device__ __forceinline__ bool start_ray(RayState& r, const TraversalParams& P, const Ray* __restrict__ rays, int id) {
+    const float4 a = dev::ldg4_stream(reinterpret_cast<const float4*>(rays + id) + 0);    // org, tmin
+    const float4 b = dev::ldg4_stream(reinterpret_cast<const float4*>(rays + id) + 1);    // dir, tmax
+    return init_ray(r, P, a, b);
 }
 
 /// Enters the cell owning the current voxel, computes where the ray leaves it
@@ -209,8 +213,15 @@ __global__ void __launch_bounds__(256) detect_raster(const Ray* __restrict__ ray
             return err <= tol;                       // NaN compares false
         };
         if (tol > 0.0f) {
-            for (int i = 2 + threadIdx.x; i < limit; i += 256)
-                if (!continues(i)) { atomicMin(&row_break, i); break; }
+            // 256 candidates per round; the block stops at the first round that holds a break
+            for (int base = 2; base < limit; base += 256) {
+                const int i = base + threadIdx.x;
+                if (i < limit && !continues(i)) atomicMin(&row_break, i);
+                __syncthreads();
+                const bool found = row_break < kScan;
+                __syncthreads();                      // everyone has read the flag before the next round writes it
+                if (found) break;
+            }
         }
         __syncthreads();
         width = row_break;
@@ -295,41 +306,47 @@ __device__ __forceinline__ int tiled_ray_index_nodiv(int tile, int lane, int wid
     return (ty * kTileH + (lane >> 3)) * width + tx * kTileW + (lane & 7);
 }
 
+/// The march of one ray through the grid after init_ray (src/traverse.cu:56-90)
+template <typename CellT>
+__device__ __forceinline__ void walk(RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
+                                     const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
+                                     const Tri* __restrict__ tris) {
+    constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
+    while (true) {
+        dev::CellBox cell;
+        const float texit = enter_cell(r, P, entries, cells, cell);
+        if (kSentinel) {
+            int cur = cell.begin;
+            int ref = cur >= 0 ? __ldg(ref_ids + cur++) : -1;
+            while (ref >= 0) {
+                const int next = __ldg(ref_ids + cur++);
+                intersect_tri(r, tris, ref);
+                ref = next;
+            }
+            r.steps += 1 + (cur - cell.begin);
+        } else {
+            int cur = cell.begin;
+            int ref = cur < cell.end ? __ldg(ref_ids + cur++) : -1;
+            while (ref >= 0) {
+                const int next = cur < cell.end ? __ldg(ref_ids + cur++) : -1;
+                intersect_tri(r, tris, ref);
+                ref = next;
+            }
+            r.steps += 1 + (cell.end - cell.begin);
+        }
+        if (r.hit_t <= texit) break;
+        // left the grid? (unsigned compare folds the < 0 test)
+        if ((unsigned(r.vx) >= unsigned(P.dims_x)) | (unsigned(r.vy) >= unsigned(P.dims_y)) | (unsigned(r.vz) >= unsigned(P.dims_z))) break;
+    }
+}
+
 template <typename CellT, bool kPrimId>
 __device__ __forceinline__ void trace_one(const TraversalParams& P, const uint32_t* __restrict__ entries,
                                           const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
                                           const Tri* __restrict__ tris, const Ray* __restrict__ rays,
                                           Hit* __restrict__ hits, int id) {
-    constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
     RayState r;
-    if (start_ray(r, P, rays, id)) {
-        while (true) {
-            dev::CellBox cell;
-            const float texit = enter_cell(r, P, entries, cells, cell);
-            if (kSentinel) {
-                int cur = cell.begin;
-                int ref = cur >= 0 ? __ldg(ref_ids + cur++) : -1;
-                while (ref >= 0) {
-                    const int next = __ldg(ref_ids + cur++);
-                    intersect_tri(r, tris, ref);
-                    ref = next;
-                }
-                r.steps += 1 + (cur - cell.begin);
-            } else {
-                int cur = cell.begin;
-                int ref = cur < cell.end ? __ldg(ref_ids + cur++) : -1;
-                while (ref >= 0) {
-                    const int next = cur < cell.end ? __ldg(ref_ids + cur++) : -1;
-                    intersect_tri(r, tris, ref);
-                    ref = next;
-                }
-                r.steps += 1 + (cell.end - cell.begin);
-            }
-            if (r.hit_t <= texit) break;
-            // left the grid? (unsigned compare folds the < 0 test)
-            if ((unsigned(r.vx) >= unsigned(P.dims_x)) | (unsigned(r.vy) >= unsigned(P.dims_y)) | (unsigned(r.vz) >= unsigned(P.dims_z))) break;
-        }
-    }
+    if (start_ray(r, P, rays, id)) walk(r, P, entries, cells, ref_ids, tris);
     finish_ray<kPrimId>(r, hits, id);
 }
 
@@ -359,6 +376,110 @@ traverse_tiles(const __grid_constant__ TraversalParams P,
         if (lane == 0) tile = first_dynamic + atomicAdd(next_tile, 1);
         tile = __shfl_sync(kAll, tile, 0);
     }
+}
+
+// ---------------------------------------------------------------------------
+// Frames from a camera (the interactive loop of src/main.cpp:591-625 without its host round trips): the
+// reference generates the primary rays on one CPU thread (gen_rays, src/main.cpp:52-66), uploads 32 B per
+// ray, traces, downloads 16 B per hit and colours the pixels on the CPU (update_surface,
+// src/main.cpp:90-111). Here a ray is generated in the registers of the thread that traces it and its
+// pixel is written by the same thread: no ray buffer, no hit buffer, 4 B per pixel leave the device.
+// The arithmetic is the host's: IEEE multiply / add / divide, no contraction (the front end is compiled
+// by g++ for x86-64 without FMA), so rays and pixels are bit-identical to the reference's.
+// ---------------------------------------------------------------------------
+struct FrameParams {
+    float eye_x, eye_y, eye_z;
+    float dir_x, dir_y, dir_z;
+    float right_x, right_y, right_z;
+    float up_x, up_y, up_z;
+    float clip;
+    int   width, height;
+};
+
+/// gen_rays for pixel (x, y): kx = 2x/w - 1, ky = 1 - 2y/h, dir = cam.dir + cam.right*kx + cam.up*ky
+__device__ __forceinline__ void camera_ray(const FrameParams& F, int x, int y, float4& a, float4& b) {
+    const float kx = __fsub_rn(__fdiv_rn(__int2float_rn(2 * x), __int2float_rn(F.width)), 1.0f);
+    const float ky = __fsub_rn(1.0f, __fdiv_rn(__int2float_rn(2 * y), __int2float_rn(F.height)));
+    a = make_float4(F.eye_x, F.eye_y, F.eye_z, 0.0f);
+    b.x = __fadd_rn(__fadd_rn(F.dir_x, __fmul_rn(F.right_x, kx)), __fmul_rn(F.up_x, ky));
+    b.y = __fadd_rn(__fadd_rn(F.dir_y, __fmul_rn(F.right_y, kx)), __fmul_rn(F.up_y, ky));
+    b.z = __fadd_rn(__fadd_rn(F.dir_z, __fmul_rn(F.right_z, kx)), __fmul_rn(F.up_z, ky));
+    b.w = F.clip;
+}
+
+/// float -> uint8_t the way the x86 front end does it: truncate to int32, keep the low byte
+__device__ __forceinline__ unsigned to_byte(float v) { return unsigned(__float2int_rz(v)) & 0xFFu; }
+
+/// update_surface (src/main.cpp:90-111): BGRA of one pixel; mode 0 = depth, 1 = steps as grey, 2 = heat map
+template <int kMode>
+__device__ __forceinline__ unsigned shade_pixel(const RayState& r, float clip) {
+    unsigned b, g, red;
+    if (kMode == 0) {
+        b = g = red = to_byte(__fdiv_rn(__fmul_rn(255.0f, r.hit_t), clip));
+    } else if (kMode == 1) {
+        b = g = red = unsigned(min(255, r.steps));
+    } else {
+        // gradient(), src/main.cpp:68-88
+        const float gx[5] = {0.0f, 0.0f, 0.0f, 255.0f, 255.0f};
+        const float gy[5] = {0.0f, 255.0f, 128.0f, 255.0f, 0.0f};
+        const float gz[5] = {255.0f, 255.0f, 0.0f, 0.0f, 0.0f};
+        const float s = 1.0f / 5;
+        const float k = __fdiv_rn(__int2float_rn(min(100, r.steps)), 100.0f);
+        const int i = min(4, __float2int_rz(__fmul_rn(k, 5.0f)));
+        const int j = min(4, i + 1);
+        const float t = __fdiv_rn(__fsub_rn(k, __fmul_rn(__int2float_rn(i), s)), s);
+        const float u = __fsub_rn(1.0f, t);
+        red = to_byte(__fadd_rn(__fmul_rn(u, gx[i]), __fmul_rn(t, gx[j])));
+        g   = to_byte(__fadd_rn(__fmul_rn(u, gy[i]), __fmul_rn(t, gy[j])));
+        b   = to_byte(__fadd_rn(__fmul_rn(u, gz[i]), __fmul_rn(t, gz[j])));
+    }
+    return b | (g << 8) | (red << 16) | 0xFF000000u;
+}
+
+/// Pixel of tile `tile`, lane `lane`: 8x4 tiles when the image allows it, scan-line order otherwise
+__device__ __forceinline__ int frame_pixel(const FrameParams& F, int tile, int lane) {
+    const bool tiled = (F.width % kTileW == 0) && (F.height % kTileH == 0);
+    return tiled ? tiled_ray_index_nodiv(tile, lane, F.width) : tile * 32 + lane;
+}
+
+/// Fused frame: generate, trace, shade. One launch, resident warps pulling tiles.
+template <typename CellT, int kMode>
+__global__ void __launch_bounds__(128, 10)
+render_tiles(const __grid_constant__ TraversalParams P, const __grid_constant__ FrameParams F,
+             const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
+             const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
+             unsigned* __restrict__ pixels, int* __restrict__ next_tile) {
+    constexpr unsigned kAll = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int num_pixels = F.width * F.height;
+    const int num_tiles = (num_pixels + 31) >> 5;
+    const int first_dynamic = gridDim.x * 4;
+    int tile = blockIdx.x * 4 + (threadIdx.x >> 5);
+    while (tile < num_tiles) {
+        if (tile * 32 + lane < num_pixels) {
+            const int id = frame_pixel(F, tile, lane);
+            const int y = id / F.width, x = id - y * F.width;
+            float4 a, b;
+            camera_ray(F, x, y, a, b);
+            RayState r;
+            if (init_ray(r, P, a, b)) walk(r, P, entries, cells, ref_ids, tris);
+            pixels[id] = shade_pixel<kMode>(r, F.clip);
+        }
+        __syncwarp();
+        if (lane == 0) tile = first_dynamic + atomicAdd(next_tile, 1);
+        tile = __shfl_sync(kAll, tile, 0);
+    }
+}
+
+/// gen_rays alone: the ray buffer the reference's front end would upload
+__global__ void __launch_bounds__(256) generate_camera_rays(const __grid_constant__ FrameParams F, Ray* __restrict__ rays) {
+    const int id = blockIdx.x * 256 + threadIdx.x;
+    if (id >= F.width * F.height) return;
+    const int y = id / F.width, x = id - y * F.width;
+    float4 a, b;
+    camera_ray(F, x, y, a, b);
+    reinterpret_cast<float4*>(rays + id)[0] = a;
+    reinterpret_cast<float4*>(rays + id)[1] = b;
 }
 
 constexpr int kBlockThreads = 128;
@@ -712,6 +833,61 @@ void setup_traversal(const Grid& grid) {
     P.cell_x = cell.x; P.cell_y = cell.y; P.cell_z = cell.z;
     P.inv_x = inv.x; P.inv_y = inv.y; P.inv_z = inv.z;
     g_params_set = true;
+}
+
+namespace {
+
+FrameParams frame_params(const FrameCamera& cam, float clip, int width, int height) {
+    FrameParams F;
+    F.eye_x = cam.eye.x; F.eye_y = cam.eye.y; F.eye_z = cam.eye.z;
+    F.dir_x = cam.dir.x; F.dir_y = cam.dir.y; F.dir_z = cam.dir.z;
+    F.right_x = cam.right.x; F.right_y = cam.right.y; F.right_z = cam.right.z;
+    F.up_x = cam.up.x; F.up_y = cam.up.y; F.up_z = cam.up.z;
+    F.clip = clip; F.width = width; F.height = height;
+    return F;
+}
+
+template <typename CellT>
+void launch_frame(const Grid& grid, const CellT* cells, const Tri* tris, const FrameParams& F, int mode, unsigned* pixels) {
+    DeviceState& st = device_state();
+    auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
+    const int num_pixels = F.width * F.height;
+    HGB_CUDA(cudaMemsetAsync(st.counter, 0, sizeof(int), 0));
+    const int blocks = std::min(st.num_sms * 10, round_div(num_pixels, 128));
+    if (mode == 0)      render_tiles<CellT, 0><<<blocks, 128>>>(g_params, F, entries, cells, grid.ref_ids, tris, pixels, st.counter);
+    else if (mode == 1) render_tiles<CellT, 1><<<blocks, 128>>>(g_params, F, entries, cells, grid.ref_ids, tris, pixels, st.counter);
+    else                render_tiles<CellT, 2><<<blocks, 128>>>(g_params, F, entries, cells, grid.ref_ids, tris, pixels, st.counter);
+    count_launch();
+    HGB_CUDA(cudaGetLastError());
+}
+
+} // namespace
+
+FrameCamera make_camera(const vec3& eye, const vec3& center, const vec3& up, float fov, float ratio) {
+    // gen_camera, src/main.cpp:42-50 (host IEEE arithmetic, libm tanf)
+    FrameCamera cam;
+    const float f = tanf(M_PI * fov / 360);
+    cam.dir = normalize(center - eye);
+    cam.right = normalize(cross(cam.dir, up)) * (f * ratio);
+    cam.up = normalize(cross(cam.right, cam.dir)) * f;
+    cam.eye = eye;
+    return cam;
+}
+
+void generate_rays(const FrameCamera& cam, float clip, int width, int height, Ray* rays) {
+    if (width <= 0 || height <= 0) return;
+    const FrameParams F = frame_params(cam, clip, width, height);
+    generate_camera_rays<<<round_div(width * height, 256), 256>>>(F, rays); count_launch();
+    HGB_CUDA(cudaGetLastError());
+}
+
+void render_frame(const Grid& grid, const Tri* tris, const FrameCamera& cam, float clip, int width, int height,
+                  int mode, unsigned* pixels) {
+    if (width <= 0 || height <= 0) return;
+    require_setup(grid);
+    const FrameParams F = frame_params(cam, clip, width, height);
+    if (grid.small_cells) launch_frame<SmallCell>(grid, grid.small_cells, tris, F, mode, pixels);
+    else                  launch_frame<Cell>(grid, grid.cells, tris, F, mode, pixels);
 }
 
 bool set_traversal_option(const char* key, int value) {

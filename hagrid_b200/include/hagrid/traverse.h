@@ -26,6 +26,23 @@ void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, 
 void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays, Hit* host_hits, int num_rays,
                         Ray* dev_rays, Hit* dev_hits, bool prim_ids);
 
+/// Camera of a frame: what gen_camera of the reference's front end produces (src/main.cpp:18-23,42-50).
+struct FrameCamera { vec3 eye, right, up, dir; };
+
+/// gen_camera (src/main.cpp:42-50), host arithmetic.
+FrameCamera make_camera(const vec3& eye, const vec3& center, const vec3& up, float fov, float ratio);
+
+/// gen_rays (src/main.cpp:52-66) on the device: width x height rays in scan-line order into the device
+/// buffer `rays`, bit-identical to the host loop. Asynchronous on the legacy default stream.
+void generate_rays(const FrameCamera& cam, float clip, int width, int height, Ray* rays);
+
+/// One frame of the reference's viewer (src/main.cpp:591-625) fused into one launch: primary rays are
+/// generated, traced and coloured on the device; `pixels` (device, width * height BGRA words) receives
+/// what update_surface (src/main.cpp:90-111) would write: mode 0 = depth, 1 = step count as grey,
+/// 2 = step count as heat map. Asynchronous on the legacy default stream. Not part of the reference API.
+void render_frame(const Grid& grid, const Tri* tris, const FrameCamera& cam, float clip, int width, int height,
+                  int mode, unsigned* pixels);
+
 /// Tuning switches: "traverse_variant" (0 = one thread per ray, 1 = persistent phase-scheduled warps,
 /// 2 = one thread per ray re-tiled 8x4 on rasters, 4 = resident warps pulling 8x4 tiles, 3 = automatic) and
 /// "host_frame_chunk_rays" (chunk size of traverse_grid_host). Returns false for unknown keys.

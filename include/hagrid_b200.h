@@ -126,6 +126,21 @@ HGB_API int  hgb_traverse_timed(hgb_scene* scene, const void* dev_rays, void* de
 HGB_API int  hgb_traverse_grid_host(hgb_scene* scene, const void* host_rays,
                             void* host_hits, int num_rays, int hit_mode);
 
+/* Camera frames: the interactive loop of the reference's front end (src/main.cpp:591-625).
+ * `cam` is 12 floats in the member order of its Camera struct (src/main.cpp:18-23): eye, right, up, dir.
+ *   hgb_make_camera    gen_camera  (src/main.cpp:42-50), host arithmetic
+ *   hgb_generate_rays  gen_rays    (src/main.cpp:52-66): width*height rays, scan-line order, into a DEVICE buffer
+ *   hgb_render_frame   gen_rays + traverse_grid + update_surface (src/main.cpp:90-111, 598-621) for one frame;
+ *                      `host_bgra` receives width*height BGRA words; display_mode 0 = depth, 1 = steps as grey,
+ *                      2 = steps as heat map (DisplayMode, src/main.cpp:34-38). This library does all three
+ *                      steps in one launch on the device; the reference build of this ABI runs the reference's own
+ *                      host loop (CPU ray generation, upload, trace, download, CPU colouring). */
+HGB_API int  hgb_make_camera(const float eye[3], const float center[3], const float up[3], float fov, float ratio,
+                             float cam_out[12]);
+HGB_API int  hgb_generate_rays(hgb_scene* scene, const float cam[12], float clip, int width, int height, void* dev_rays);
+HGB_API int  hgb_render_frame(hgb_scene* scene, const float cam[12], float clip, int width, int height,
+                              int display_mode, void* host_bgra);
+
 /* Grid inspection / transplant (parity tests move a grid between the
  * reference build and this library through host memory). */
 HGB_API int  hgb_grid_get_info(const hgb_scene* scene, hgb_grid_info* info);

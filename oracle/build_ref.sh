@@ -52,8 +52,11 @@ wait
 CXXFLAGS="-O2 -DNDEBUG -DHOST= -DDEVICE= -fPIC -w -I/usr/local/cuda/include"
 g++ -std=c++11 $CXXFLAGS -I"$W" -I"$ROOT/include" -DHGB_REFERENCE_BUILD -fvisibility=hidden \
     -c "$ROOT/hagrid_b200/csrc/c_api.cpp" -o c_api.o
+# the reference's front-end functions (gen_camera, gen_rays, update_surface): src/main.cpp included unmodified
+g++ -std=c++11 $CXXFLAGS -I"$HERE/sdl_stub" -I"$W" -fvisibility=hidden -c "$HERE/ref_frontend.cpp" -o ref_frontend.o
+g++ -std=c++11 $CXXFLAGS -I"$W" -fvisibility=hidden -c load_obj.cpp -o load_obj_pic.o
 # c_api.o needs default visibility for the hagrid:: symbols it imports from the objects above
-g++ -shared -o "$OUT/libhagrid_ref.so" c_api.o build.o merge.o flatten.o expand.o compress.o mem_manager.o profile.o \
+g++ -shared -o "$OUT/libhagrid_ref.so" c_api.o ref_frontend.o load_obj_pic.o build.o merge.o flatten.o expand.o compress.o mem_manager.o profile.o \
     traverse.o traverse_pid.o -Wl,-Bsymbolic -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 g++ -std=c++11 $CXXFLAGS -I"$HERE/sdl_stub" -I"$W" -c main.cpp -o main.o
 g++ -std=c++11 $CXXFLAGS -I"$W" -c load_obj.cpp -o load_obj.o

@@ -820,3 +820,67 @@ int og_compress(og_grid* g) {
     g->cells = NULL; g->small_cells = sc; g->refs = refs; g->num_refs = at; g->compressed = 1;
     return 1;
 }
+
+/* ------------------------------------------------------------------ front-end host functions (src/main.cpp:42-111)
+ * Pinned against the reference's own code: tests/golden/frontend.npz is produced by oracle/ref_frontend.cpp,
+ * which includes src/main.cpp unmodified (tests/golden/make_frontend_golden.py). */
+static void normalize3(float* v) {                                             /* src/vec.h: a * (1 / length(a)) */
+    const float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const float inv = 1.0f / len;
+    v[0] *= inv; v[1] *= inv; v[2] *= inv;
+}
+static void cross3(const float* a, const float* b, float* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+/* gen_camera, src/main.cpp:42-50; cam = eye, right, up, dir (member order of Camera, src/main.cpp:18-23) */
+void og_gen_camera(const float* eye, const float* center, const float* up, float fov, float ratio, float* cam) {
+    const float f = tanf(M_PI * fov / 360);
+    float* right = cam + 3; float* upv = cam + 6; float* dir = cam + 9;
+    for (int k = 0; k < 3; k++) { cam[k] = eye[k]; dir[k] = center[k] - eye[k]; }
+    normalize3(dir);
+    cross3(dir, up, right); normalize3(right);
+    const float fr = f * ratio;
+    for (int k = 0; k < 3; k++) right[k] *= fr;
+    cross3(right, dir, upv); normalize3(upv);
+    for (int k = 0; k < 3; k++) upv[k] *= f;
+}
+
+/* gen_rays, src/main.cpp:52-66 */
+void og_gen_rays(const float* cam, float clip, int w, int h, og_ray* rays) {
+    const float* eye = cam; const float* right = cam + 3; const float* up = cam + 6; const float* dir = cam + 9;
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+        const float kx = 2 * x / (float)w - 1;
+        const float ky = 1 - 2 * y / (float)h;
+        og_ray* r = rays + (size_t)y * w + x;
+        for (int k = 0; k < 3; k++) {
+            r->org[k] = eye[k];
+            r->dir[k] = (dir[k] + right[k] * kx) + up[k] * ky;
+        }
+        r->tmin = 0.0f; r->tmax = clip;
+    }
+}
+
+/* update_surface<mode> + gradient, src/main.cpp:68-111, on a tightly packed BGRA image; mode 0 depth, 1 grey, 2 heat */
+void og_update_surface(int mode, const og_hit* hits, float clip, int w, int h, uint8_t* bgra) {
+    static const float g[5][3] = {{0, 0, 255}, {0, 255, 255}, {0, 128, 0}, {255, 255, 0}, {255, 0, 0}};
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        uint8_t* px = bgra + 4 * i;
+        if (mode == 0) {
+            const uint8_t c = (uint8_t)(int)(255.0f * hits[i].t / clip);
+            px[0] = px[1] = px[2] = c;
+        } else if (mode == 1) {
+            const uint8_t c = (uint8_t)imin(255, hits[i].id);
+            px[0] = px[1] = px[2] = c;
+        } else {
+            const float s = 1.0f / 5;
+            const float k = imin(100, hits[i].id) / 100.0f;
+            const int a = imin(4, (int)(k * 5)), b = imin(4, a + 1);
+            const float t = (k - a * s) / s;
+            float c[3];
+            for (int q = 0; q < 3; q++) c[q] = (1.0f - t) * g[a][q] + t * g[b][q];
+            px[0] = (uint8_t)(int)c[2]; px[1] = (uint8_t)(int)c[1]; px[2] = (uint8_t)(int)c[0];
+        }
+        px[3] = 255;
+    }
+}

@@ -52,6 +52,9 @@ def dll():
         _dll.og_compress.argtypes = [P]
         _dll.og_compress.restype = C.c_int
         _dll.og_traverse.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _dll.og_gen_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        _dll.og_gen_rays.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
+        _dll.og_update_surface.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
         _dll.og_traverse_record.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _dll.og_traverse_record_cells.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return _dll
@@ -124,3 +127,30 @@ class Grid:
         out = np.empty((rays.shape[0], max_steps), dtype=np.int32)
         dll().og_traverse_record_cells(self.ptr, tris.ctypes.data, rays.ctypes.data, out.ctypes.data, max_steps, rays.shape[0])
         return out
+
+
+RAY_DTYPE = np.dtype([("org", "<f4", 3), ("tmin", "<f4"), ("dir", "<f4", 3), ("tmax", "<f4")])
+
+
+def gen_camera(eye, center, up, fov: float, ratio: float) -> np.ndarray:
+    """gen_camera (src/main.cpp:42-50): 12 floats eye, right, up, dir."""
+    e, c, u = (np.ascontiguousarray(v, dtype="<f4") for v in (eye, center, up))
+    cam = np.empty(12, dtype="<f4")
+    dll().og_gen_camera(e.ctypes.data, c.ctypes.data, u.ctypes.data, fov, ratio, cam.ctypes.data)
+    return cam
+
+
+def gen_rays(cam: np.ndarray, clip: float, width: int, height: int) -> np.ndarray:
+    """gen_rays (src/main.cpp:52-66)."""
+    cam = np.ascontiguousarray(cam, dtype="<f4")
+    rays = np.empty(width * height, dtype=RAY_DTYPE)
+    dll().og_gen_rays(cam.ctypes.data, clip, width, height, rays.ctypes.data)
+    return rays
+
+
+def update_surface(mode: int, hits: np.ndarray, clip: float, width: int, height: int) -> np.ndarray:
+    """update_surface (src/main.cpp:90-111): (height, width, 4) BGRA bytes."""
+    hits = np.ascontiguousarray(hits)
+    out = np.empty((height, width, 4), dtype=np.uint8)
+    dll().og_update_surface(mode, hits.ctypes.data, clip, width, height, out.ctypes.data)
+    return out
