@@ -56,6 +56,13 @@ _SIGNATURES = {
     "hgb_scene_create": (C.c_void_p, [C.c_int, C.c_int]),
     "hgb_scene_destroy": (None, [C.c_void_p]),
     "hgb_scene_set_tris": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hgb_scene_load_obj": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "hgb_obj_parse": (C.c_void_p, [C.c_char_p, C.c_int]),
+    "hgb_obj_num_vertices": (C.c_int, [C.c_void_p]),
+    "hgb_obj_num_tris": (C.c_int, [C.c_void_p]),
+    "hgb_obj_vertices": (C.c_void_p, [C.c_void_p]),
+    "hgb_obj_indices": (C.c_void_p, [C.c_void_p]),
+    "hgb_obj_free": (None, [C.c_void_p]),
     "hgb_scene_num_tris": (C.c_int, [C.c_void_p]),
     "hgb_scene_peak_bytes": (C.c_size_t, [C.c_void_p]),
     "hgb_build_grid": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
@@ -134,6 +141,22 @@ def make_camera(eye, center, up, fov: float, ratio: float, lib: "Library | None"
     return cam
 
 
+def parse_obj(path, threads: int = 0, lib: "Library | None" = None):
+    """Host half of the ingest: (vertices (n, 3) float32 with the dummy vertex at index 0, indices (t, 3) int32)."""
+    lib = lib or library()
+    h = lib.dll.hgb_obj_parse(str(path).encode(), threads)
+    if not h:
+        raise HagridError(lib.dll.hgb_last_error().decode())
+    try:
+        nv, nt = lib.dll.hgb_obj_num_vertices(h), lib.dll.hgb_obj_num_tris(h)
+        verts = np.frombuffer((C.c_char * (12 * nv)).from_address(lib.dll.hgb_obj_vertices(h)), dtype="<f4").reshape(nv, 3).copy()
+        idx = (np.frombuffer((C.c_char * (12 * nt)).from_address(lib.dll.hgb_obj_indices(h)), dtype="<i4").reshape(nt, 3).copy()
+               if nt else np.empty((0, 3), dtype="<i4"))
+        return verts, idx
+    finally:
+        lib.dll.hgb_obj_free(h)
+
+
 _default_library: Library | None = None
 
 
@@ -159,11 +182,18 @@ def _ptr(x) -> int:
 class Scene:
     """MemManager + device triangles + Grid, as src/main.cpp:471-478 sets them up."""
 
-    def __init__(self, tris: np.ndarray, device: int = 0, keep_alive: bool = False, lib: Library | None = None):
+    def __init__(self, tris, device: int = 0, keep_alive: bool = False, lib: Library | None = None, threads: int = 0):
+        """`tris`: (n,) triangle records, or the path of a Wavefront OBJ file (load_model, src/main.cpp:246-275)."""
         self.lib = lib or library()
         self._h = None
         if self.lib.device_count() <= device:
             raise HagridError(f"CUDA device {device} not available (hagrid_b200 has no CPU fallback)")
+        if isinstance(tris, (str, Path)):
+            self._h = self.lib.dll.hgb_scene_create(device, int(keep_alive))
+            if not self._h:
+                raise HagridError(self.lib.dll.hgb_last_error().decode())
+            self.num_tris = self.lib.check(self.lib.dll.hgb_scene_load_obj(self._h, str(tris).encode(), threads), "load_obj")
+            return
         tris = np.ascontiguousarray(tris)
         if tris.dtype != TRI_DTYPE:
             tris = tris.astype("<f4", copy=False).reshape(-1, 12).view(TRI_DTYPE).reshape(-1)
@@ -280,6 +310,11 @@ class Scene:
         assert entries.shape[0] == gi.num_entries and cells.shape[0] == gi.num_cells and refs.shape[0] == gi.num_refs
         self.lib.check(self.lib.dll.hgb_grid_upload(self._h, C.byref(gi), _ptr(entries), _ptr(cells), _ptr(refs)),
                        "grid_upload")
+
+    def download_tris(self) -> np.ndarray:
+        tris = np.empty(self.num_tris, dtype=TRI_DTYPE)
+        self.lib.check(self.lib.dll.hgb_grid_download(self._h, ARRAY_TRIS, _ptr(tris), tris.nbytes), "download tris")
+        return tris
 
     def peak_bytes(self) -> int:
         return int(self.lib.dll.hgb_scene_peak_bytes(self._h))

@@ -27,6 +27,9 @@
 extern "C" void hgb_ref_gen_camera(const float* eye, const float* center, const float* up, float fov, float ratio, float* cam12);
 extern "C" const void* hgb_ref_gen_rays(const float* cam12, float clip, int w, int h);
 extern "C" void hgb_ref_update_surface(int mode, const void* hits, float clip, int w, int h, void* bgra);
+extern "C" const void* hgb_ref_load_model(const char* path, int* num_tris);
+#else
+#include "scene_ingest.h"
 #endif
 
 namespace hagrid {
@@ -194,6 +197,62 @@ int hgb_scene_set_tris(hgb_scene* s, const void* host_tris, int num_tris) {
     s->num_tris = num_tris;
     return 0;
 }
+
+int hgb_scene_load_obj(hgb_scene* s, const char* path, int threads) {
+    if (!bind(s)) return -1;
+    if (!path) return fail("load_obj: null path");
+#ifdef HGB_REFERENCE_BUILD
+    (void)threads;
+    int n = 0;
+    const Tri* host = static_cast<const Tri*>(hgb_ref_load_model(path, &n));
+    if (!host || n <= 0) return fail("load_obj: the reference's load_model refused the file");
+    s->mem.free(s->tris);
+    s->tris = s->mem.alloc<Tri>(n);
+    s->mem.copy<Copy::HST_TO_DEV>(s->tris, host, n);
+    s->num_tris = n;
+    return n;
+#else
+    ObjGeometry geo;
+    if (!parse_obj(path, threads, geo)) { g_error = "load_obj: " + geo.error; return -1; }
+    const int n = int(geo.indices.size() / 3);
+    if (n <= 0) return fail("load_obj: no triangles");
+    vec3* dev_vertices = s->mem.alloc<vec3>(geo.vertices.size());
+    int* dev_indices = s->mem.alloc<int>(geo.indices.size());
+    s->mem.copy<Copy::HST_TO_DEV>(dev_vertices, geo.vertices.data(), geo.vertices.size());
+    s->mem.copy<Copy::HST_TO_DEV>(dev_indices, geo.indices.data(), geo.indices.size());
+    s->mem.free(s->tris);
+    s->tris = s->mem.alloc<Tri>(n);
+    setup_triangles(dev_vertices, dev_indices, n, s->tris);
+    cudaDeviceSynchronize();
+    s->mem.free(dev_vertices);
+    s->mem.free(dev_indices);
+    s->num_tris = n;
+    return n;
+#endif
+}
+
+#ifdef HGB_REFERENCE_BUILD
+struct hgb_obj { int unused; };
+hgb_obj* hgb_obj_parse(const char*, int) { g_error = "obj_parse: not part of the reference build"; return nullptr; }
+int hgb_obj_num_vertices(const hgb_obj*) { return 0; }
+int hgb_obj_num_tris(const hgb_obj*) { return 0; }
+const float* hgb_obj_vertices(const hgb_obj*) { return nullptr; }
+const int* hgb_obj_indices(const hgb_obj*) { return nullptr; }
+void hgb_obj_free(hgb_obj*) {}
+#else
+struct hgb_obj { ObjGeometry geo; };
+hgb_obj* hgb_obj_parse(const char* path, int threads) {
+    if (!path) { g_error = "obj_parse: null path"; return nullptr; }
+    hgb_obj* obj = new hgb_obj;
+    if (!parse_obj(path, threads, obj->geo)) { g_error = "obj_parse: " + obj->geo.error; delete obj; return nullptr; }
+    return obj;
+}
+int hgb_obj_num_vertices(const hgb_obj* obj) { return obj ? int(obj->geo.vertices.size()) : 0; }
+int hgb_obj_num_tris(const hgb_obj* obj) { return obj ? int(obj->geo.indices.size() / 3) : 0; }
+const float* hgb_obj_vertices(const hgb_obj* obj) { return obj ? reinterpret_cast<const float*>(obj->geo.vertices.data()) : nullptr; }
+const int* hgb_obj_indices(const hgb_obj* obj) { return obj ? obj->geo.indices.data() : nullptr; }
+void hgb_obj_free(hgb_obj* obj) { delete obj; }
+#endif
 
 int hgb_scene_num_tris(const hgb_scene* s) { return s ? s->num_tris : 0; }
 size_t hgb_scene_peak_bytes(const hgb_scene* s) { return s ? s->mem.max_usage() : 0; }

@@ -1,0 +1,195 @@
+// Parallel Wavefront OBJ parser with the semantics of the reference's single-threaded loader
+// (src/load_obj.cpp:78-239) for everything that reaches the tracer: positions and faces.
+//
+//   * the file is read once and cut into one chunk per thread at line boundaries;
+//   * pass 1 (parallel): every chunk parses its lines with the reference's rules — `v` positions via strtof,
+//     `f` faces via the reference's index grammar (v, v/t, v//n, v/t/n, negative = relative, at most 8 corners),
+//     `vn` / `vt` are only counted (relative t / n indices are validated against the counts), g / o / s /
+//     usemtl / mtllib are accepted, anything else is an error like in the reference (err_count > 0 => refused);
+//   * the per-chunk vertex / normal / texcoord counts are prefix-summed, then pass 2 (parallel) resolves the
+//     relative indices, validates them and writes the fan triangles (v0, v[i+1], v[i+2]) of every face to its
+//     final place. Faces keep file order, which is the order load_model emits them in (src/main.cpp:251-270).
+//
+// Differences from the reference, all on inputs it mishandles: a position index beyond the vertices of the
+// file is an error here (the reference reads out of bounds); a line of 1023 characters or more ends the parse
+// like the reference's failed getline does (src/load_obj.cpp:103-105), but is reported as an error.
+#include <algorithm>
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#include "scene_ingest.h"
+
+namespace hagrid {
+
+namespace {
+
+constexpr int kMaxCorners = 8;      // Face::max_indices, src/load_obj.h
+constexpr size_t kMaxLine = 1024;   // src/load_obj.cpp:102
+
+struct RawFace {
+    int v[kMaxCorners], t[kMaxCorners], n[kMaxCorners];
+    int count;
+    int verts_before, texs_before, norms_before;   // chunk-local counts when the face was read
+};
+
+struct Chunk {
+    const char* begin; const char* end;
+    std::vector<vec3> vertices;
+    std::vector<RawFace> faces;
+    int num_normals = 0, num_texcoords = 0;
+    int first_vertex = 0, first_normal = 0, first_texcoord = 0;   // global counts before the chunk
+    size_t first_tri = 0, num_tris = 0;
+    std::string error;
+};
+
+inline const char* skip_spaces(const char* p) { while (std::isspace((unsigned char)*p)) p++; return p; }
+
+/// read_index, src/load_obj.cpp:42-76
+bool read_corner(const char*& p, int& v, int& t, int& n) {
+    const char* base = skip_spaces(p);
+    if (!std::isdigit((unsigned char)*base) && *base != '-') return false;
+    v = t = n = 0;
+    char* next;
+    v = int(std::strtol(base, &next, 10)); base = skip_spaces(next);
+    if (*base == '/') {
+        base++;
+        if (*base != '/') { t = int(std::strtol(base, &next, 10)); base = next; }
+        base = skip_spaces(base);
+        if (*base == '/') { base++; n = int(std::strtol(base, &next, 10)); base = next; }
+    }
+    p = base;
+    return true;
+}
+
+void parse_chunk(Chunk& c) {
+    char line[kMaxLine];
+    const char* p = c.begin;
+    while (p < c.end) {
+        const char* eol = static_cast<const char*>(std::memchr(p, '\n', size_t(c.end - p)));
+        const char* stop = eol ? eol : c.end;
+        const size_t len = size_t(stop - p);
+        if (len >= kMaxLine - 1) { c.error = "line longer than 1022 characters"; return; }
+        std::memcpy(line, p, len);
+        line[len] = '\0';
+        p = eol ? eol + 1 : c.end;
+
+        const char* ptr = skip_spaces(line);
+        if (*ptr == '\0' || *ptr == '#') continue;
+        {   // remove_eol, src/load_obj.cpp:22-30
+            char* q = const_cast<char*>(ptr);
+            int i = int(std::strlen(q)) - 1;
+            while (i > 0 && std::isspace((unsigned char)q[i])) q[i--] = '\0';
+        }
+        if (*ptr == 'v') {
+            if (ptr[1] == ' ' || ptr[1] == '\t') {
+                char* next;
+                vec3 v;
+                v.x = std::strtof(ptr + 1, &next); v.y = std::strtof(next, &next); v.z = std::strtof(next, &next);
+                c.vertices.push_back(v);
+            } else if (ptr[1] == 'n') c.num_normals++;
+            else if (ptr[1] == 't') c.num_texcoords++;
+            else { c.error = "invalid vertex"; return; }
+        } else if (*ptr == 'f' && std::isspace((unsigned char)ptr[1])) {
+            RawFace f;
+            f.count = 0;
+            const char* q = ptr + 2;
+            while (f.count < kMaxCorners && read_corner(q, f.v[f.count], f.t[f.count], f.n[f.count])) f.count++;
+            if (f.count < 3) { c.error = "invalid face"; return; }
+            f.verts_before = int(c.vertices.size()); f.texs_before = c.num_texcoords; f.norms_before = c.num_normals;
+            c.faces.push_back(f);
+        } else if ((*ptr == 'g' || *ptr == 'o' || *ptr == 's') && std::isspace((unsigned char)ptr[1])) {
+        } else if ((!std::strncmp(ptr, "usemtl", 6) || !std::strncmp(ptr, "mtllib", 6)) && std::isspace((unsigned char)ptr[6])) {
+        } else { c.error = std::string("unknown command ") + ptr; return; }
+    }
+}
+
+/// Relative -> absolute indices and validation (src/load_obj.cpp:172-187); sizes include the dummy element 0.
+bool resolve_face(const Chunk& c, const RawFace& f, int total_vertices, int* abs_v) {
+    const int nv = 1 + c.first_vertex + f.verts_before, nt = 1 + c.first_texcoord + f.texs_before, nn = 1 + c.first_normal + f.norms_before;
+    for (int i = 0; i < f.count; i++) {
+        const int v = f.v[i] < 0 ? nv + f.v[i] : f.v[i];
+        const int t = f.t[i] < 0 ? nt + f.t[i] : f.t[i];
+        const int n = f.n[i] < 0 ? nn + f.n[i] : f.n[i];
+        if (v <= 0 || t < 0 || n < 0 || v > total_vertices) return false;     // positive indices may point ahead in the file
+        abs_v[i] = v;
+    }
+    return true;
+}
+
+template <typename F>
+void run_parallel(int count, F&& body) {
+    std::vector<std::thread> pool;
+    for (int i = 1; i < count; i++) pool.emplace_back([&body, i] { body(i); });
+    body(0);
+    for (auto& t : pool) t.join();
+}
+
+} // namespace
+
+bool parse_obj(const std::string& path, int threads, ObjGeometry& out) {
+    out.vertices.clear(); out.indices.clear(); out.error.clear();
+    std::FILE* fp = std::fopen(path.c_str(), "rb");
+    if (!fp) { out.error = "cannot open " + path; return false; }
+    std::fseek(fp, 0, SEEK_END);
+    const long size = std::ftell(fp);
+    std::fseek(fp, 0, SEEK_SET);
+    std::vector<char> text(size_t(size) + 1);
+    const size_t got = size > 0 ? std::fread(text.data(), 1, size_t(size), fp) : 0;
+    std::fclose(fp);
+    if (got != size_t(size)) { out.error = "cannot read " + path; return false; }
+    text[size_t(size)] = '\0';
+
+    if (threads <= 0) threads = int(std::thread::hardware_concurrency());
+    threads = std::max(1, std::min(threads, int(size / (1 << 16)) + 1));
+    std::vector<Chunk> chunks;
+    chunks.resize(static_cast<size_t>(threads));
+    {
+        const char* base = text.data();
+        const char* end = base + size;
+        const char* cur = base;
+        for (int i = 0; i < threads; i++) {
+            const char* want = i + 1 == threads ? end : base + size_t(size) * size_t(i + 1) / size_t(threads);
+            if (want < cur) want = cur;
+            if (want < end) {
+                const char* nl = static_cast<const char*>(std::memchr(want, '\n', size_t(end - want)));
+                want = nl ? nl + 1 : end;
+            }
+            chunks[size_t(i)].begin = cur; chunks[size_t(i)].end = want;
+            cur = want;
+        }
+    }
+    run_parallel(threads, [&](int i) { parse_chunk(chunks[size_t(i)]); });
+    for (const Chunk& c : chunks)
+        if (!c.error.empty()) { out.error = c.error; return false; }
+
+    int nv = 0, nn = 0, nt = 0;
+    size_t tris = 0;
+    for (Chunk& c : chunks) {
+        c.first_vertex = nv; c.first_normal = nn; c.first_texcoord = nt; c.first_tri = tris;
+        nv += int(c.vertices.size()); nn += c.num_normals; nt += c.num_texcoords;
+        for (const RawFace& f : c.faces) c.num_tris += size_t(f.count - 2);
+        tris += c.num_tris;
+    }
+    if (tris > size_t(0x7fffffff) / 3) { out.error = "too many triangles"; return false; }
+    out.vertices.resize(size_t(nv) + 1);
+    out.vertices[0] = vec3(0.0f, 0.0f, 0.0f);          // dummy vertex, src/load_obj.cpp:96
+    out.indices.resize(tris * 3);
+    run_parallel(threads, [&](int i) {
+        Chunk& c = chunks[size_t(i)];
+        if (!c.vertices.empty()) std::memcpy(&out.vertices[size_t(c.first_vertex) + 1], c.vertices.data(), sizeof(vec3) * c.vertices.size());
+        int* dst = out.indices.data() + 3 * c.first_tri;
+        for (const RawFace& f : c.faces) {
+            int v[kMaxCorners];
+            if (!resolve_face(c, f, nv, v)) { c.error = "invalid indices"; return; }
+            for (int k = 0; k < f.count - 2; k++) { *dst++ = v[0]; *dst++ = v[k + 1]; *dst++ = v[k + 2]; }
+        }
+    });
+    for (const Chunk& c : chunks)
+        if (!c.error.empty()) { out.error = c.error; return false; }
+    return true;
+}
+
+} // namespace hagrid

@@ -89,6 +89,21 @@ HGB_API hgb_scene* hgb_scene_create(int device, int keep_alive);
 HGB_API void       hgb_scene_destroy(hgb_scene* scene);
 /* `host_tris`: num_tris x 48 B {v0,nx,e1,ny,e2,nz} (prims.h:13-16). */
 HGB_API int  hgb_scene_set_tris(hgb_scene* scene, const void* host_tris, int num_tris);
+/* Scene ingest: load_model of the front end (src/main.cpp:246-275) = ObjLoader::load_obj (src/load_obj.cpp:78-239)
+ * + fan triangulation + triangle setup. This library parses the file with `threads` host threads (0 = all) and
+ * builds the 48-byte records on the device; the reference build of this ABI runs the reference's own
+ * single-threaded load_model and uploads the result. Returns the number of triangles, negative on error
+ * (unreadable file, or anything the reference's loader counts as an error). */
+HGB_API int  hgb_scene_load_obj(hgb_scene* scene, const char* path, int threads);
+/* The host half of the ingest on its own (no device needed): positions (index 0 = the loader's dummy vertex,
+ * src/load_obj.cpp:96) and three position indices per fan triangle, in file order. */
+typedef struct hgb_obj hgb_obj;
+HGB_API hgb_obj*     hgb_obj_parse(const char* path, int threads);       /* NULL on error, see hgb_last_error() */
+HGB_API int          hgb_obj_num_vertices(const hgb_obj* obj);
+HGB_API int          hgb_obj_num_tris(const hgb_obj* obj);
+HGB_API const float* hgb_obj_vertices(const hgb_obj* obj);               /* 3 floats per vertex */
+HGB_API const int*   hgb_obj_indices(const hgb_obj* obj);                /* 3 ints per triangle */
+HGB_API void         hgb_obj_free(hgb_obj* obj);
 HGB_API int  hgb_scene_num_tris(const hgb_scene* scene);
 /* Peak bytes handed out by the scene's MemManager (mem_manager.h:104). */
 HGB_API size_t hgb_scene_peak_bytes(const hgb_scene* scene);

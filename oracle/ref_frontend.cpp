@@ -37,6 +37,17 @@ const void* hgb_ref_gen_rays(const float* cam12, float clip, int w, int h) {
     return rays.data();
 }
 
+/// load_model (src/main.cpp:246-275): the reference's OBJ loader + triangle setup; nullptr when it refuses the file
+__attribute__((visibility("default")))
+const void* hgb_ref_load_model(const char* path, int* num_tris) {
+    static std::vector<Tri> tris;
+    tris.clear();
+    *num_tris = 0;
+    if (!load_model(path, tris)) return nullptr;
+    *num_tris = int(tris.size());
+    return tris.data();
+}
+
 /// update_surface<mode> on a tightly packed w x h BGRA image
 __attribute__((visibility("default")))
 void hgb_ref_update_surface(int mode, const void* hits, float clip, int w, int h, void* bgra) {
