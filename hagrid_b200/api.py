@@ -80,6 +80,11 @@ _SIGNATURES = {
     "hgb_make_camera": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
     "hgb_generate_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "hgb_render_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hgb_rays_file_count": (C.c_longlong, [C.c_char_p]),
+    "hgb_load_rays": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_float, C.c_float, C.c_void_p]),
+    "hgb_save_rays": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
+    "hgb_grid_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "hgb_grid_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "hgb_grid_get_info": (C.c_int, [C.c_void_p, C.POINTER(GridInfo)]),
     "hgb_grid_download": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "hgb_grid_upload": (C.c_int, [C.c_void_p, C.POINTER(GridInfo), C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -281,6 +286,36 @@ class Scene:
             out = np.empty((height, width, 4), dtype=np.uint8)
         self.lib.check(self.lib.dll.hgb_render_frame(self._h, _ptr(cam), clip, width, height, mode, _ptr(out)), "render_frame")
         return out
+
+    # --- on-disk formats ------------------------------------------------------------
+    def load_rays(self, path, tmin: float = 0.0, tmax: float = float(np.finfo(np.float32).max)) -> np.ndarray:
+        """load_rays (src/main.cpp:277-300) to the device, downloaded again: (n,) rays."""
+        n = int(self.lib.dll.hgb_rays_file_count(str(path).encode()))
+        if n < 0:
+            raise HagridError(f"cannot open {path}")
+        d_rays = self.device_alloc(max(n, 1) * 32)
+        try:
+            got = self.lib.check(int(self.lib.dll.hgb_load_rays(self._h, str(path).encode(), tmin, tmax, d_rays)), "load_rays")
+            assert got == n
+            return self.to_host(np.empty(n, dtype=RAY_DTYPE), d_rays) if n else np.empty(0, dtype=RAY_DTYPE)
+        finally:
+            self.device_free(d_rays)
+
+    def save_rays(self, path, rays: np.ndarray):
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == RAY_DTYPE
+        d_rays = self.device_alloc(max(rays.nbytes, 32))
+        try:
+            self.to_device(d_rays, rays)
+            self.lib.check(self.lib.dll.hgb_save_rays(self._h, str(path).encode(), d_rays, rays.shape[0]), "save_rays")
+        finally:
+            self.device_free(d_rays)
+
+    def save_grid(self, path):
+        self.lib.check(self.lib.dll.hgb_grid_save(self._h, str(path).encode()), "grid_save")
+
+    def load_grid(self, path):
+        self.lib.check(self.lib.dll.hgb_grid_load(self._h, str(path).encode()), "grid_load")
 
     # --- grid inspection / transplant -------------------------------------------
     def info(self) -> GridInfo:

@@ -28,7 +28,9 @@ extern "C" void hgb_ref_gen_camera(const float* eye, const float* center, const 
 extern "C" const void* hgb_ref_gen_rays(const float* cam12, float clip, int w, int h);
 extern "C" void hgb_ref_update_surface(int mode, const void* hits, float clip, int w, int h, void* bgra);
 extern "C" const void* hgb_ref_load_model(const char* path, int* num_tris);
+extern "C" const void* hgb_ref_load_rays(const char* path, float tmin, float tmax, long long* count);
 #else
+#include "formats.h"
 #include "scene_ingest.h"
 #endif
 
@@ -432,6 +434,70 @@ int hgb_render_frame(hgb_scene* s, const float cam[12], float clip, int width, i
     s->mem.copy<Copy::DEV_TO_HST>(static_cast<unsigned*>(host_bgra), s->frame_pixels, n);
 #endif
     return 0;
+}
+
+long long hgb_rays_file_count(const char* path) {
+    if (!path) return -1;
+    std::FILE* fp = std::fopen(path, "rb");
+    if (!fp) return -1;
+    std::fseek(fp, 0, SEEK_END);
+    const long long n = std::ftell(fp) / 24;                  // src/main.cpp:282
+    std::fclose(fp);
+    return n;
+}
+
+long long hgb_load_rays(hgb_scene* s, const char* path, float tmin, float tmax, void* dev_rays) {
+    if (!bind(s)) return -1;
+    if (!path || !dev_rays) return fail("load_rays: null argument");
+#ifdef HGB_REFERENCE_BUILD
+    long long n = 0;
+    const Ray* host = static_cast<const Ray*>(hgb_ref_load_rays(path, tmin, tmax, &n));
+    if (!host) return fail("load_rays: cannot load ray file");
+    if (n > 0) s->mem.copy<Copy::HST_TO_DEV>(static_cast<Ray*>(dev_rays), host, size_t(n));
+    return n;
+#else
+    const long long n = load_rays_to_device(s->mem, path, tmin, tmax, static_cast<Ray*>(dev_rays));
+    if (n < 0) return fail("load_rays: cannot load ray file");
+    return n;
+#endif
+}
+
+int hgb_save_rays(hgb_scene* s, const char* path, const void* dev_rays, long long count) {
+    if (!bind(s)) return -1;
+    if (!path || (!dev_rays && count > 0) || count < 0) return fail("save_rays: bad argument");
+#ifdef HGB_REFERENCE_BUILD
+    return fail("save_rays: the reference has no ray file writer");
+#else
+    return save_rays_from_device(s->mem, path, static_cast<const Ray*>(dev_rays), count) ? 0 : fail("save_rays: cannot write file");
+#endif
+}
+
+int hgb_grid_save(hgb_scene* s, const char* path) {
+    if (!bind(s)) return -1;
+    if (!path) return fail("grid_save: null path");
+#ifdef HGB_REFERENCE_BUILD
+    return fail("grid_save: the reference has no grid serialisation");
+#else
+    std::string err;
+    if (!save_grid(s->mem, path, s->grid, err)) { g_error = "grid_save: " + err; return -1; }
+    return 0;
+#endif
+}
+
+int hgb_grid_load(hgb_scene* s, const char* path) {
+    if (!bind(s)) return -1;
+    if (!path) return fail("grid_load: null path");
+#ifdef HGB_REFERENCE_BUILD
+    return fail("grid_load: the reference has no grid serialisation");
+#else
+    Grid loaded;
+    loaded.entries = nullptr; loaded.cells = nullptr; loaded.small_cells = nullptr; loaded.ref_ids = nullptr;
+    std::string err;
+    if (!load_grid(s->mem, path, loaded, err)) { g_error = "grid_load: " + err; return -1; }
+    release_grid(s);
+    s->grid = loaded;
+    return 0;
+#endif
 }
 
 int hgb_grid_get_info(const hgb_scene* s, hgb_grid_info* info) {

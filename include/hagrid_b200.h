@@ -156,6 +156,17 @@ HGB_API int  hgb_generate_rays(hgb_scene* scene, const float cam[12], float clip
 HGB_API int  hgb_render_frame(hgb_scene* scene, const float cam[12], float clip, int width, int height,
                               int display_mode, void* host_bgra);
 
+/* On-disk formats. `.rays` is the reference's ray file (6 float32 per ray: org, dir; tmin / tmax come from the
+ * caller; load_rays, src/main.cpp:277-300). hgb_load_rays fills a DEVICE buffer of hgb_rays_file_count() rays:
+ * this library uploads the 24-byte records and expands them on the device, the reference build of this ABI runs
+ * the reference's own load_rays and uploads 32-byte rays. `.hgrid` is this library's grid cache (the reference
+ * has no serialisation); hgb_grid_load replaces the scene's grid, arrays come from its MemManager. */
+HGB_API long long hgb_rays_file_count(const char* path);                 /* -1: cannot open */
+HGB_API long long hgb_load_rays(hgb_scene* scene, const char* path, float tmin, float tmax, void* dev_rays);
+HGB_API int  hgb_save_rays(hgb_scene* scene, const char* path, const void* dev_rays, long long count);
+HGB_API int  hgb_grid_save(hgb_scene* scene, const char* path);
+HGB_API int  hgb_grid_load(hgb_scene* scene, const char* path);
+
 /* Grid inspection / transplant (parity tests move a grid between the
  * reference build and this library through host memory). */
 HGB_API int  hgb_grid_get_info(const hgb_scene* scene, hgb_grid_info* info);

@@ -48,6 +48,18 @@ const void* hgb_ref_load_model(const char* path, int* num_tris) {
     return tris.data();
 }
 
+/// load_rays (src/main.cpp:277-300); nullptr when the file cannot be opened
+__attribute__((visibility("default")))
+const void* hgb_ref_load_rays(const char* path, float tmin, float tmax, long long* count) {
+    static std::vector<Ray> rays;
+    rays.clear();
+    *count = 0;
+    if (!load_rays(path, rays, tmin, tmax)) return nullptr;
+    *count = (long long)rays.size();
+    static Ray none;
+    return rays.empty() ? &none : rays.data();
+}
+
 /// update_surface<mode> on a tightly packed w x h BGRA image
 __attribute__((visibility("default")))
 void hgb_ref_update_surface(int mode, const void* hits, float clip, int w, int h, void* bgra) {
