@@ -304,6 +304,77 @@ def test_rays_missing_the_grid_and_degenerate_rays(lib):
     sc.close()
 
 
+def test_awkward_rays_match_the_reference_bit_for_bit(lib, ref_lib):
+    """Rays that stress the discrete decisions of the march (src/traverse.cu:42-90): axis-aligned and zero
+    direction components (safe_rcp = +-inf), origins exactly on voxel and cell planes, origins outside the
+    grid, tmin > 0, short tmax, negative tmin, denormal components (flushed to zero by FTZ), huge coordinates."""
+    tris = scenes.small_mixed(20000, seed=41)
+    a, b = Scene(tris, lib=ref_lib), Scene(tris, lib=lib)
+    a.build_all(0.15, 3.0); b.build_all(0.15, 3.0)
+    info = b.info().as_dict()
+    lo, hi = np.array(info["bbox_min"], np.float32), np.array(info["bbox_max"], np.float32)
+    vdims = np.array(info["dims"]) << info["shift"]
+    rng = np.random.default_rng(99)
+    n = 60000
+    rays = scenes.random_rays(tris, n, seed=17, tmax=50.0)
+    k = n // 10
+    axes = rng.integers(0, 3, k)
+    rays["dir"][:k] = 0.0                                              # axis-aligned: two zero components
+    rays["dir"][np.arange(k), axes] = rng.choice([-1.0, 1.0], k)
+    rays["dir"][k:2 * k, rng.integers(0, 3)] = 0.0                     # one zero component
+    rays["dir"][2 * k:3 * k, 0] = np.float32(1e-41)                    # denormal: zero under FTZ
+    rays["dir"][3 * k:4 * k, 1] = -0.0
+    cell = (hi - lo) / vdims                                           # origins exactly on voxel planes
+    rays["org"][4 * k:5 * k] = lo + cell * rng.integers(0, vdims, (k, 3)).astype(np.float32)
+    rays["org"][5 * k:6 * k] = lo + (hi - lo) * rng.choice([-0.5, 0.0, 1.0, 1.5], (k, 3)).astype(np.float32)   # on / outside the box
+    rays["tmin"][6 * k:7 * k] = rng.random(k).astype(np.float32) * 3.0
+    rays["tmax"][6 * k:7 * k] = rays["tmin"][6 * k:7 * k] + rng.random(k).astype(np.float32)
+    rays["tmin"][7 * k:8 * k] = -5.0                                   # hits behind the origin become eligible
+    rays["org"][8 * k:9 * k] *= np.float32(1e6)                        # far away, mostly missing the grid
+    rays["tmax"][9 * k:] = np.float32(1e-3)
+    for compress in (False, True):
+        if compress:
+            assert a.compress_grid() and b.compress_grid()
+        a.setup_traversal()
+        want = {m: a.trace(rays, m) for m in (HIT_PRIM_ID, HIT_STEPS)}
+        b.setup_traversal()
+        try:
+            for v in VARIANTS:
+                lib.set_option("traverse_variant", v)
+                for m in (HIT_PRIM_ID, HIT_STEPS):
+                    got = b.trace(rays, m)
+                    assert np.array_equal(got["id"], want[m]["id"]), (compress, v, m)
+                    assert np.array_equal(got["t"].view(np.uint32), want[m]["t"].view(np.uint32)), (compress, v, m)
+        finally:
+            lib.set_option("traverse_variant", 3)
+    a.close(); b.close()
+
+
+def test_awkward_scenes_build_like_the_reference(lib, ref_lib):
+    """Degenerate and duplicated triangles, axis-aligned sheets, a wide range of triangle sizes: every
+    construction stage byte-identical to the reference."""
+    rng = np.random.default_rng(5)
+    base = scenes.small_mixed(6000, seed=8)
+    v0, v1, v2 = scenes.tri_vertices(base)
+    v0, v1, v2 = v0.copy(), v1.copy(), v2.copy()
+    v1[:300] = v0[:300]                                    # zero-area: two coincident corners
+    v2[300:600] = v0[300:600] + (v1[300:600] - v0[300:600]) * np.float32(2.0)     # zero-area: collinear
+    v0[600:900, 1] = v1[600:900, 1] = v2[600:900, 1] = np.float32(0.5)            # axis-aligned sheet
+    scale = np.float32(10.0) ** rng.uniform(-3, 0, 300).astype(np.float32)        # tiny triangles
+    c = (v0[900:1200] + v1[900:1200] + v2[900:1200]) / np.float32(3)
+    for v in (v0, v1, v2):
+        v[900:1200] = c + (v[900:1200] - c) * scale[:, None]
+    tris = np.concatenate([scenes.make_tris(v0, v1, v2), base[:500]])             # + exact duplicates
+    a, b = Scene(tris, lib=ref_lib), Scene(tris, lib=lib)
+    a.build_grid(0.12, 2.4); b.build_grid(0.12, 2.4)
+    for stage in ("build", "merge", "flatten", "expand", "compress"):
+        if stage != "build":
+            getattr(a, stage + "_grid")(); getattr(b, stage + "_grid")()
+        ia, aa = dump(a); ib, ab = dump(b)
+        assert grid_diff(ib, ab, (ia,) + aa) == [], stage
+    a.close(); b.close()
+
+
 def test_single_and_degenerate_triangles(lib):
     tris = scenes.make_tris([[0, 0, 0], [0, 0, 0]], [[1, 0, 0], [0, 0, 0]], [[0, 1, 0], [0, 0, 0]])   # second one is a point
     from oracle import oracle
