@@ -538,6 +538,7 @@ constexpr int kBlockThreads = 128;
 // ---------------------------------------------------------------------------
 constexpr int kVoteBlock = 32;          // rays reserved per atomic
 constexpr int kVoteRefillMinLanes = 4;
+constexpr int kVoteTurn = 3;            // references a lane tests per triangle turn
 constexpr int kVoteBlocksPerSm = 10;    // <= 51 registers
 
 template <typename CellT, bool kPrimId>
@@ -592,7 +593,7 @@ traverse_voting(const __grid_constant__ TraversalParams P,
 
         const unsigned walkers = __ballot_sync(kAll, ray_id >= 0 && ref < 0);
         const unsigned testers = __ballot_sync(kAll, ref >= 0);
-        if (__popc(walkers) >= __popc(testers)) {
+        if (__popc(walkers) >= __popc(testers)) {        // weighted votes (2:1 ... 1:2) measured slower
             if (ray_id >= 0 && ref < 0) {
                 dev::CellBox cell;
                 texit = enter_cell(r, P, entries, cells, cell);
@@ -611,11 +612,21 @@ traverse_voting(const __grid_constant__ TraversalParams P,
                 }
             }
         } else if (ref >= 0) {
-            int next;
-            if (kSentinel) { next = __ldg(ref_ids + cur++); r.steps++; }
-            else           { next = cur < end ? __ldg(ref_ids + cur++) : -1; }
-            intersect_tri(r, tris, ref);
-            ref = next;
+            // up to kVoteTurn references per turn: their triangles' loads are in flight together
+            int batch[kVoteTurn];
+            batch[0] = ref;
+#pragma unroll
+            for (int k = 1; k <= kVoteTurn; k++) {
+                int next = -1;
+                if (batch[k - 1] >= 0) {
+                    if (kSentinel) { next = __ldg(ref_ids + cur++); r.steps++; }
+                    else           { next = cur < end ? __ldg(ref_ids + cur++) : -1; }
+                }
+                if (k < kVoteTurn) batch[k] = next; else ref = next;
+            }
+#pragma unroll
+            for (int k = 0; k < kVoteTurn; k++)
+                if (batch[k] >= 0) intersect_tri(r, tris, batch[k]);
             if (ref < 0 && (r.hit_t <= texit || outside(r, P))) {
                 finish_ray<kPrimId>(r, hits, ray_id);
                 ray_id = -1;
