@@ -289,7 +289,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src, "kernel": ("traverse_pid<Cell, Tri>" if reference else "traverse_tiles<Cell, 1>") + " (the only kernel of a step)",
                          "algorithmic_bytes_per_launch": algo_bytes,
-                         "note": "instruction-issue-bound gather kernel (ncu: 77 % of peak issue rate, 23 of 32 lanes active): the scene "
+                         "note": "gather kernel bound by instruction issue and dependent-load latency (ncu: 70 % of peak issue rate, 22 of 32 lanes active): the scene "
                                  "lives in L2, compulsory HBM traffic is 48 B/ray; see DESIGN.md section 5"},
             "build_ms": {"mean": round(float(build_ms.mean()), 3), "min": round(float(build_ms.min()), 3),
                          "what": "build+merge+flatten+expand, keep-alive, event-timed like src/main.cpp:494-508"},
