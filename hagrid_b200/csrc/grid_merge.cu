@@ -42,6 +42,12 @@ struct MergeParams {
 
 template <int axis> __device__ __forceinline__ int pick(int x, int y, int z) { return axis == 0 ? x : (axis == 1 ? y : z); }
 
+/// Cell count of the grid a pass works on. The counts of a pass (cells in the high word, references in the
+/// low word: the totals of its scan) stay on the device and feed the next pass directly; the host only reads
+/// them once per round of three passes, for the termination test, and launches every pass of the round over
+/// the cell count it knew at the round's start (cells can only get fewer).
+__device__ __forceinline__ int live_cells(const unsigned long long* __restrict__ live) { return int(__ldg(live) >> 32); }
+
 /// |A u B| counted by the reference's two-pointer walk (src/merge.cu:58-69). The
 /// lists are only sorted for cells of even octree depth; the walk is reproduced
 /// literally because its result on unsorted input decides merges too.
@@ -84,10 +90,10 @@ template <int axis>
 __global__ void __launch_bounds__(kBlock) pair_up(const __grid_constant__ MergeParams P, const uint32_t* __restrict__ entries,
                                                   const Cell* __restrict__ cells, const int* __restrict__ refs,
                                                   int* __restrict__ merge_counts, int* __restrict__ nexts, int* __restrict__ prevs,
-                                                  int empty_mask, int num_cells) {
+                                                  int empty_mask, const unsigned long long* __restrict__ live) {
     using namespace dev;
     const int id = blockIdx.x * kBlock + threadIdx.x;
-    if (id >= num_cells) return;
+    if (id >= live_cells(live)) return;
     const CellBox c1 = load_cell_box(cells, id);
     const int n1 = c1.end - c1.begin;
     int count = -(n1 + 1);
@@ -145,9 +151,9 @@ __global__ void __launch_bounds__(kBlock) pair_up(const __grid_constant__ MergeP
 /// src/merge.cu:146-187).
 __global__ void __launch_bounds__(kBlock) resolve_chains(const int* __restrict__ nexts, const int* __restrict__ prevs,
                                                          const int* __restrict__ merge_counts, int* __restrict__ kept,
-                                                         int* __restrict__ new_counts, int num_cells) {
+                                                         int* __restrict__ new_counts, const unsigned long long* __restrict__ live) {
     const int id = blockIdx.x * kBlock + threadIdx.x;
-    if (id >= num_cells || prevs[id] >= 0) return;
+    if (id >= live_cells(live) || prevs[id] >= 0) return;
     int cur = id;
     bool keep = true;
     while (cur >= 0) {
@@ -159,10 +165,13 @@ __global__ void __launch_bounds__(kBlock) resolve_chains(const int* __restrict__
     }
 }
 
+/// Scanned over the host's upper bound of the cell count: slots past the live count contribute nothing
 struct KeptAndCount {
     const int* kept;
     const int* new_counts;
+    const unsigned long long* live;
     __device__ __forceinline__ unsigned long long operator()(int i) const {
+        if (i >= live_cells(live)) return 0ull;
         return ((unsigned long long)kept[i] << 32) | (unsigned)new_counts[i];
     }
 };
@@ -173,13 +182,13 @@ __global__ void __launch_bounds__(kBlock) merge_cells(const __grid_constant__ Me
                                                       const Cell* __restrict__ cells, const int* __restrict__ refs,
                                                       const unsigned long long* __restrict__ scan, const int* __restrict__ merge_counts,
                                                       int* __restrict__ new_cell_ids, Cell* __restrict__ new_cells,
-                                                      int* __restrict__ new_refs, int num_cells) {
+                                                      int* __restrict__ new_refs, const unsigned long long* __restrict__ live) {
     using namespace dev;
     const int id = blockIdx.x * kBlock + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int src0 = 0, n0 = 0, src1 = 0, n1 = 0, dst = 0;     // list(s) this lane has to write
     bool two_way = false;
-    if (id < num_cells) {
+    if (id < live_cells(live)) {
         const unsigned long long here = scan[id], after = scan[id + 1];
         const int new_id = int(here >> 32);
         if (int(after >> 32) > new_id) {                  // survivor
@@ -242,23 +251,21 @@ struct MergeBuffers {
 };
 
 template <int axis>
-void merge_pass(const MergeParams& P, Grid& grid, Cell*& spare_cells, int*& spare_refs, int empty_mask, MergeBuffers& b) {
-    const int num_cells = grid.num_cells;
+void merge_pass(const MergeParams& P, Grid& grid, Cell*& spare_cells, int*& spare_refs, int empty_mask, MergeBuffers& b,
+                int bound, int pass) {
     auto entries = reinterpret_cast<uint32_t*>(grid.entries);
-    HGB_CUDA(cudaMemsetAsync(b.prevs, 0xFF, sizeof(int) * num_cells, 0));
-    pair_up<axis><<<blocks_for(num_cells), kBlock>>>(P, entries, grid.cells, grid.ref_ids, b.merge_counts, b.nexts, b.prevs, empty_mask, num_cells); count_launch();
-    resolve_chains<<<blocks_for(num_cells), kBlock>>>(b.nexts, b.prevs, b.merge_counts, b.kept, b.new_counts, num_cells); count_launch();
-    prim::exclusive_scan<unsigned long long>(KeptAndCount{b.kept, b.new_counts}, num_cells, b.scan, b.scan_tmp, b.totals);
-    unsigned long long totals = 0;
-    HGB_CUDA(cudaMemcpy(&totals, b.totals, sizeof(totals), cudaMemcpyDeviceToHost));
-    merge_cells<axis><<<blocks_for(num_cells), kBlock>>>(P, entries, grid.cells, grid.ref_ids, b.scan, b.merge_counts, b.new_cell_ids,
-                                                         spare_cells, spare_refs, num_cells); count_launch();
+    const unsigned long long* live = b.totals + (pass & 1);          // counts the previous pass left
+    unsigned long long* next = b.totals + ((pass + 1) & 1);
+    HGB_CUDA(cudaMemsetAsync(b.prevs, 0xFF, sizeof(int) * size_t(bound), 0));
+    pair_up<axis><<<blocks_for(bound), kBlock>>>(P, entries, grid.cells, grid.ref_ids, b.merge_counts, b.nexts, b.prevs, empty_mask, live); count_launch();
+    resolve_chains<<<blocks_for(bound), kBlock>>>(b.nexts, b.prevs, b.merge_counts, b.kept, b.new_counts, live); count_launch();
+    prim::exclusive_scan<unsigned long long>(KeptAndCount{b.kept, b.new_counts, live}, bound, b.scan, b.scan_tmp, next);
+    merge_cells<axis><<<blocks_for(bound), kBlock>>>(P, entries, grid.cells, grid.ref_ids, b.scan, b.merge_counts, b.new_cell_ids,
+                                                     spare_cells, spare_refs, live); count_launch();
     remap_entries<<<blocks_for(grid.num_entries), kBlock>>>(entries, b.new_cell_ids, grid.num_entries); count_launch();
     HGB_CUDA(cudaGetLastError());
     std::swap(spare_cells, grid.cells);
     std::swap(spare_refs, grid.ref_ids);
-    grid.num_cells = int(totals >> 32);
-    grid.num_refs = int(totals & 0xFFFFFFFFu);
 }
 
 } // namespace
@@ -278,8 +285,8 @@ void merge_grid(MemManager& mem, Grid& grid, float alpha) {
     b.new_counts = mem.alloc<int>(n);
     b.new_cell_ids = mem.alloc<int>(n);
     b.scan = mem.alloc<unsigned long long>(n);
-    b.scan_tmp = mem.alloc<unsigned long long>(prim::num_tiles(grid.num_cells) + 2);
-    b.totals = b.scan_tmp + prim::num_tiles(grid.num_cells) + 1;
+    b.scan_tmp = mem.alloc<unsigned long long>(prim::num_tiles(grid.num_cells) + 3);
+    b.totals = b.scan_tmp + prim::num_tiles(grid.num_cells) + 1;       // two slots, used alternately
 
     const vec3 extents = grid.bbox.extents();
     const ivec3 dims = grid.dims << grid.shift;
@@ -290,14 +297,19 @@ void merge_grid(MemManager& mem, Grid& grid, float alpha) {
     P.shift = grid.shift;
     P.cell_x = cell_size.x; P.cell_y = cell_size.y; P.cell_z = cell_size.z;
 
-    if (alpha > 0) {
-        int before, round = 0;
+    if (alpha > 0 && grid.num_cells > 0) {
+        unsigned long long totals = ((unsigned long long)grid.num_cells << 32) | (unsigned)grid.num_refs;
+        HGB_CUDA(cudaMemcpy(b.totals, &totals, sizeof(totals), cudaMemcpyHostToDevice));
+        int before, round = 0, pass = 0;
         do {
             before = grid.num_cells;
             const int mask = round > 3 ? 0 : (1 << (round + 1)) - 1;
-            merge_pass<0>(P, grid, spare_cells, spare_refs, mask, b);
-            merge_pass<1>(P, grid, spare_cells, spare_refs, mask, b);
-            merge_pass<2>(P, grid, spare_cells, spare_refs, mask, b);
+            merge_pass<0>(P, grid, spare_cells, spare_refs, mask, b, before, pass++);
+            merge_pass<1>(P, grid, spare_cells, spare_refs, mask, b, before, pass++);
+            merge_pass<2>(P, grid, spare_cells, spare_refs, mask, b, before, pass++);
+            HGB_CUDA(cudaMemcpy(&totals, b.totals + (pass & 1), sizeof(totals), cudaMemcpyDeviceToHost));     // the round's only sync
+            grid.num_cells = int(totals >> 32);
+            grid.num_refs = int(totals & 0xFFFFFFFFu);
             round++;
         } while (grid.num_cells < alpha * before);
     }

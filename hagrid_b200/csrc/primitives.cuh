@@ -3,7 +3,8 @@
 // DevicePartition / DeviceRadixSort, src/parallel.cuh:12-89).
 //
 //   * exclusive_scan<T>(): reduce-then-scan over 2048-element tiles with a
-//     fused input functor; T = int or a packed 64-bit pair of counters. The
+//     fused input functor, two launches (the block that finishes the reduce
+//     last also scans the tile sums); T = int or a packed 64-bit pair of counters. The
 //     total stays on the device (no host round trip per call, unlike
 //     parallel.cuh:40); callers fetch several totals with one copy.
 //   * sort_pairs(): stable LSD radix sort, 8 bits per pass, warp-match
@@ -65,23 +66,14 @@ __device__ __forceinline__ T block_exclusive_sum(T v, T* smem, T& total) {
 }
 
 // ------------------------------------------------------------------ scan
-template <typename T, typename F>
-__global__ void __launch_bounds__(kThreads) scan_reduce_tiles(F f, int n, T* __restrict__ tile_sums) {
-    __shared__ T smem[kThreads / 32 + 1];
-    const int base = blockIdx.x * kTile + threadIdx.x * kItems;
-    T sum = 0;
-#pragma unroll
-    for (int k = 0; k < kItems; k++)
-        if (base + k < n) sum += f(base + k);
-    T total;
-    block_exclusive_sum(sum, smem, total);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
+/// Blocks of scan_reduce_tiles take a ticket when their tile sum is visible; the block that draws the last
+/// one scans the tile sums (nobody waits for anybody: the last block simply arrives last) and puts the
+/// ticket counter back to zero for the next scan on the stream.
+static __device__ unsigned int g_scan_tickets;
 
-/// In-place exclusive scan of `sums[0, count)` by one block; writes the grand total.
+/// In-place exclusive scan of `sums[0, count)` by the calling block; writes the grand total.
 template <typename T>
-__global__ void __launch_bounds__(kThreads) scan_tile_sums(T* __restrict__ sums, int count, T* __restrict__ total_out) {
-    __shared__ T smem[kThreads / 32 + 1];
+__device__ __forceinline__ void block_scan_tile_sums(T* sums, int count, T* total_out, T* smem) {
     T carry = 0;
     for (int start = 0; start < count; start += kTile) {
         const int base = start + threadIdx.x * kItems;
@@ -89,7 +81,7 @@ __global__ void __launch_bounds__(kThreads) scan_tile_sums(T* __restrict__ sums,
         T sum = 0;
 #pragma unroll
         for (int k = 0; k < kItems; k++) {
-            v[k] = base + k < count ? sums[base + k] : T(0);
+            v[k] = base + k < count ? __ldcg(sums + base + k) : T(0);      // written by other blocks of this launch
             sum += v[k];
         }
         T total;
@@ -102,6 +94,29 @@ __global__ void __launch_bounds__(kThreads) scan_tile_sums(T* __restrict__ sums,
         carry += total;
     }
     if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(kThreads) scan_reduce_tiles(F f, int n, T* __restrict__ tile_sums, T* __restrict__ total_out) {
+    __shared__ T smem[kThreads / 32 + 1];
+    __shared__ bool last_block;
+    const int base = blockIdx.x * kTile + threadIdx.x * kItems;
+    T sum = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; k++)
+        if (base + k < n) sum += f(base + k);
+    T total;
+    block_exclusive_sum(sum, smem, total);
+    if (threadIdx.x == 0) {
+        tile_sums[blockIdx.x] = total;
+        __threadfence();                                        // the sum is visible before the ticket is drawn
+        last_block = atomicAdd(&g_scan_tickets, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last_block) return;
+    __threadfence();
+    block_scan_tile_sums(tile_sums, int(gridDim.x), total_out, smem);
+    if (threadIdx.x == 0) g_scan_tickets = 0;
 }
 
 template <typename T, typename F>
@@ -137,8 +152,7 @@ void exclusive_scan(F f, int n, T* out, T* tile_scratch, T* total_out) {
         return;
     }
     const int tiles = num_tiles(n);
-    scan_reduce_tiles<T, F><<<tiles, kThreads>>>(f, n, tile_scratch); count_launch();
-    scan_tile_sums<T><<<1, kThreads>>>(tile_scratch, tiles, total_out); count_launch();
+    scan_reduce_tiles<T, F><<<tiles, kThreads>>>(f, n, tile_scratch, total_out); count_launch();
     scan_apply_tiles<T, F><<<tiles, kThreads>>>(f, n, tile_scratch, out); count_launch();
     HGB_CUDA(cudaGetLastError());
 }
