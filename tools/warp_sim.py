@@ -50,8 +50,7 @@ def main():
         thread_cells += (seqs >= 0).sum(); thread_tris += seqs[seqs > 0].sum(); nw += 1
         for k, (c, t) in simulate(seqs).items():
             a = tot.setdefault(k, [0, 0]); a[0] += c; a[1] += t
-    print(f"{nw} warps: per-thread cells {thread_cells / nw / 32:.2f} tris {thread_tris / nw / 32:.2f}; empty-cell share "
-          f"{1 - 0:.0f}")
+    print(f"{nw} warps: per-thread cells {thread_cells / nw / 32:.2f} tris {thread_tris / nw / 32:.2f}")
     for k, (c, t) in tot.items():
         print(f"{k:12s} cell iters/warp {c / nw:6.2f} tri iters/warp {t / nw:6.2f}  cost {(c * CELL + t * TRI) / nw:8.0f}")
 
