@@ -248,57 +248,7 @@ __global__ void __launch_bounds__(256) detect_raster(const Ray* __restrict__ ray
 }
 
 // ---------------------------------------------------------------------------
-// Kernel A: one thread per ray, optionally re-tiled (coherent buffers).
-// ---------------------------------------------------------------------------
-template <typename CellT, bool kPrimId>
-__global__ void __launch_bounds__(128)
-traverse_per_thread(const __grid_constant__ TraversalParams P,
-                    const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
-                    const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
-                    const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
-                    const int* __restrict__ layout, int host_width) {
-    constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
-    int id = threadIdx.x + blockDim.x * blockIdx.x;
-    if (id >= num_rays) return;
-    {   // raster width: found on the device (layout word) or already known to the host
-        const int width = layout ? __ldg(layout) : host_width;
-        if (width > 0) id = tiled_ray_index(id, width);
-    }
-    RayState r;
-    if (start_ray(r, P, rays, id)) {
-        while (true) {
-            dev::CellBox cell;
-            const float texit = enter_cell(r, P, entries, cells, cell);
-            if (kSentinel) {
-                int cur = cell.begin;
-                int ref = cur >= 0 ? __ldg(ref_ids + cur++) : -1;
-                while (ref >= 0) {
-                    const int next = __ldg(ref_ids + cur++);
-                    intersect_tri(r, tris, ref);
-                    ref = next;
-                }
-                r.steps += 1 + (cur - cell.begin);
-            } else {
-                int cur = cell.begin;
-                int ref = cur < cell.end ? __ldg(ref_ids + cur++) : -1;
-                while (ref >= 0) {
-                    const int next = cur < cell.end ? __ldg(ref_ids + cur++) : -1;
-                    intersect_tri(r, tris, ref);
-                    ref = next;
-                }
-                r.steps += 1 + (cell.end - cell.begin);
-            }
-            if (r.hit_t <= texit || outside(r, P)) break;
-        }
-    }
-    finish_ray<kPrimId>(r, hits, id);
-}
-
-// ---------------------------------------------------------------------------
-// Kernel A2: resident warps pull 32-ray tiles from a global counter (coherent buffers). Same per-ray
-// loop as kernel A; what changes is residency: a block of kernel A keeps its four warp slots until its
-// slowest warp is done (61 % achieved occupancy in ncu against 75 % theoretical), here a warp that is
-// done takes the next tile, so every warp slot of the SM stays busy until the counter runs out.
+// The march of one ray (shared by all kernels) and the tile index of the resident-warp kernels.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int tiled_ray_index_nodiv(int tile, int lane, int width) {
     // tile / (width / 8) by a float estimate and one fix-up step each way (tile < 2^24 keeps it within +-1)
@@ -346,6 +296,26 @@ __device__ __forceinline__ void trace_one(const TraversalParams& P, const uint32
     finish_ray<kPrimId>(r, hits, id);
 }
 
+// ---------------------------------------------------------------------------
+// Kernel A: one thread per ray, optionally re-tiled. The plain mapping of the reference (variant 0) and
+// its tiled form (variant 2), kept as the baselines the resident-warp kernels are measured against.
+// ---------------------------------------------------------------------------
+template <typename CellT, bool kPrimId>
+__global__ void __launch_bounds__(128)
+traverse_per_thread(const __grid_constant__ TraversalParams P,
+                    const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
+                    const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
+                    const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
+                    const int* __restrict__ layout, int host_width) {
+    int id = threadIdx.x + blockDim.x * blockIdx.x;
+    if (id >= num_rays) return;
+    {   // raster width: found on the device (layout word) or already known to the host
+        const int width = layout ? __ldg(layout) : host_width;
+        if (width > 0) id = tiled_ray_index(id, width);
+    }
+    trace_one<CellT, kPrimId>(P, entries, cells, ref_ids, tris, rays, hits, id);
+}
+
 /// Direction octant of a ray (bit k set: component k >= 0, the test enter_cell makes)
 __device__ __forceinline__ int octant_of(const RayState& r) {
     return (r.dx >= 0.0f ? 1 : 0) | (r.dy >= 0.0f ? 2 : 0) | (r.dz >= 0.0f ? 4 : 0);
@@ -381,6 +351,12 @@ __device__ __forceinline__ void walk_warp(bool ok, RayState& r, const TraversalP
     }
 }
 
+// ---------------------------------------------------------------------------
+// Kernel A2: resident warps pull 32-ray tiles from a global counter (coherent buffers). Same per-ray
+// march as kernel A; what changes is residency — a block of kernel A keeps its four warp slots until its
+// slowest warp is done, here a warp that is done takes the next tile — and the march itself, which the
+// warp picks specialised for its direction octant when all its rays share one (walk_warp).
+// ---------------------------------------------------------------------------
 constexpr int kTileBlock = 128;
 constexpr int kTileBlocksPerSm = 10;     // <= 51 registers: 40 resident warps per SM, measured best of 8 / 10 / 12
 
