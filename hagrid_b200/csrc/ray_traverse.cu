@@ -195,9 +195,9 @@ __device__ __forceinline__ int tiled_ray_index(int thread, int width) {
 __global__ void __launch_bounds__(256) detect_raster(const Ray* __restrict__ rays, int n, int* __restrict__ layout,
                                                      volatile int* __restrict__ layout_host) {
     __shared__ int row_break;
-    __shared__ int bad;
-    constexpr int kScan = 16384;
-    if (threadIdx.x == 0) { row_break = kScan; bad = 0; }
+    __shared__ int bad, misses;
+    constexpr int kScan = 16384, kSpot = 1024;
+    if (threadIdx.x == 0) { row_break = kScan; bad = 0; misses = 0; }
     __syncthreads();
     int width = 0;
     if (n >= 4 * 64) {
@@ -232,14 +232,21 @@ __global__ void __launch_bounds__(256) detect_raster(const Ray* __restrict__ ray
         const bool shape_ok = tol > 0.0f && width < kScan && width >= 64 && width % kTileW == 0 && n % width == 0 &&
                               (n / width) % kTileH == 0;
         if (shape_ok) {
-            // the second and the last row must continue with the same step
+            // the second and the last row must continue with the same step ...
             for (int k = threadIdx.x; k < 62; k += 256) {
                 if (!continues(width + 1 + k)) atomicOr(&bad, 1);
                 if (!continues(n - width + 1 + k)) atomicOr(&bad, 1);
             }
+            // ... and so must the buffer as a whole: kSpot positions spread over it (row starts skipped). A frame of
+            // secondary rays often begins and ends with rows of re-emitted camera rays; its interior does not pass.
+            for (int k = threadIdx.x; k < kSpot; k += 256) {
+                int i = int((long long)n * k / kSpot) + 1 + (k * 37) % 61;
+                if (i >= n) i = n - 1;
+                if (i % width != 0 && !continues(i)) atomicAdd(&misses, 1);
+            }
         }
         __syncthreads();
-        if (!shape_ok || bad) width = 0;
+        if (!shape_ok || bad || misses > kSpot / 16) width = 0;
     }
     if (threadIdx.x == 0) {
         layout[0] = width;
@@ -325,16 +332,16 @@ __device__ __forceinline__ int octant_of(const RayState& r) {
 /// the same direction octant — the rule for an 8x4 tile of camera rays — the warp takes the loop specialised
 /// for it, otherwise the generic one. Same cells, same triangles, same order either way.
 template <typename CellT>
-__device__ __forceinline__ void walk_warp(bool ok, RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
+__device__ __forceinline__ bool walk_warp(bool ok, RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
                                           const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
                                           const Tri* __restrict__ tris) {
     constexpr unsigned kAll = 0xFFFFFFFFu;
     const unsigned marching = __ballot_sync(kAll, ok);
-    if (marching == 0) return;
+    if (marching == 0) return true;
     const int oct = octant_of(r);
     const int first = __shfl_sync(kAll, oct, __ffs(marching) - 1);
     const bool uniform = __all_sync(kAll, !ok || oct == first);
-    if (!ok) return;
+    if (!ok) return uniform;
     if (uniform) {
         switch (first) {
             case 0: walk<CellT, 0>(r, P, entries, cells, ref_ids, tris); break;
@@ -349,6 +356,7 @@ __device__ __forceinline__ void walk_warp(bool ok, RayState& r, const TraversalP
     } else {
         walk<CellT, -1>(r, P, entries, cells, ref_ids, tris);
     }
+    return uniform;
 }
 
 // ---------------------------------------------------------------------------
@@ -366,9 +374,14 @@ traverse_tiles(const __grid_constant__ TraversalParams P,
                const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
-               const int* __restrict__ layout, int host_width, int* __restrict__ next_tile) {
+               const int* __restrict__ layout, int host_width, int* __restrict__ next_tile, int* __restrict__ feedback) {
     constexpr unsigned kAll = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
+    // feedback (device memory, may be null): [0] += warps whose rays did not share a direction octant, [1] += 1
+    // per launch. A buffer of camera rays has a few such warps along the image axes; a buffer whose warps are
+    // mostly mixed is not what this kernel is for: the host copies the words back now and then and moves such a
+    // buffer to the incoherent kernel.
+    if (feedback && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(feedback + 1, 1);
     const int width = layout ? __ldg(layout) : host_width;
     const int num_tiles = (num_rays + 31) >> 5;
     const int first_dynamic = gridDim.x * (kTileBlock / 32);
@@ -382,7 +395,8 @@ traverse_tiles(const __grid_constant__ TraversalParams P,
             if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
             ok = start_ray(r, P, rays, id);
         }
-        walk_warp(ok, r, P, entries, cells, ref_ids, tris);
+        const bool uniform = walk_warp(ok, r, P, entries, cells, ref_ids, tris);
+        if (!uniform && feedback && lane == 0) atomicAdd(feedback, 1);
         if (live) finish_ray<kPrimId>(r, hits, id);
         __syncwarp();
         if (lane == 0) tile = first_dynamic + atomicAdd(next_tile, 1);
@@ -618,6 +632,12 @@ struct DeviceState {
     int* layout_host = nullptr;      // pinned, mapped copy of layout[0]; -1 = detection still in flight
     const void* seen_rays = nullptr; // buffer the layout belongs to
     int seen_count = -1;
+    int seen_class = -1;             // -1: detection in flight, 0: incoherent, > 0: raster of that width
+    int* feedback_host = nullptr;    // pinned copy of feedback_dev, refreshed by an 8-byte async copy every few launches
+    int* feedback_dev = nullptr;     // device: [0] mixed-octant warps, [1] launches of traverse_tiles (see there)
+    int  feedback_tick = 0;
+    int feedback_mixed = 0, feedback_launches = 0;   // counter values when the current buffer was armed
+    bool feedback_armed = false;
     int num_sms = 0;
     // host-buffer frames (traverse_grid_host): one upload stream, one download stream, two traversal streams
     static constexpr int kStreams = 4, kMaxChunks = 64;
@@ -639,8 +659,10 @@ DeviceState& device_state() {
         HGB_CUDA(cudaMalloc(&st.counter, 128));
         st.layout = st.counter + 16;
         HGB_CUDA(cudaMemset(st.counter, 0, 128));
-        HGB_CUDA(cudaHostAlloc(&st.layout_host, sizeof(int), cudaHostAllocMapped));
-        *st.layout_host = 0;
+        HGB_CUDA(cudaHostAlloc(&st.layout_host, 4 * sizeof(int), cudaHostAllocMapped));
+        st.layout_host[0] = st.layout_host[1] = st.layout_host[2] = st.layout_host[3] = 0;
+        st.feedback_host = st.layout_host + 2;
+        st.feedback_dev = st.counter + 24;
         HGB_CUDA(cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     return st;
@@ -681,13 +703,14 @@ int traverse_variant() {
 /// `layout[0]` (device) or `host_width`.
 template <typename CellT, bool kPrimId>
 void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays,
-             int variant, const int* layout, int host_width, int* counter, int num_sms, cudaStream_t stream) {
+             int variant, const int* layout, int host_width, int* counter, int num_sms, cudaStream_t stream,
+             int* feedback = nullptr) {
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
     if (variant == 4) {
         HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
         const int blocks = min(num_sms * kTileBlocksPerSm, round_div(num_rays, kTileBlock));
         traverse_tiles<CellT, kPrimId><<<blocks, kTileBlock, 0, stream>>>(
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, counter); count_launch();
+            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, counter, feedback); count_launch();
     } else if (variant == 1) {
         HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
         // every warp reserves two blocks of rays up front: no more warps than there are blocks
@@ -724,21 +747,58 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
     require_setup(grid);
     DeviceState& st = device_state();
     int variant = traverse_variant();
+    int* feedback = nullptr;
     if (variant >= 2 && variant <= 4) {
-        if (rays != st.seen_rays || num_rays != st.seen_count) {
-            // new buffer: look at its layout on the device, asynchronously; this launch
-            // reads the answer from device memory, later launches also know it on the host
-            *static_cast<volatile int*>(st.layout_host) = -1;
+        // What kind of buffer is this? A new one (other address or size) is looked at on the device,
+        // asynchronously: this launch reads the answer from device memory, later launches know it on the host.
+        // A buffer known as a raster is not looked at again — the tile kernel reports when its contents stop
+        // behaving like one (feedback words) — and a buffer known as incoherent is looked at before every
+        // launch (a 10 us kernel in front of one that takes several hundred): callers reuse ray buffers.
+        volatile int* answer = st.layout_host;
+        volatile int* fb = st.feedback_host;
+        const bool same = rays == st.seen_rays && num_rays == st.seen_count;
+        if (!same) { st.seen_class = -1; st.feedback_armed = false; }
+        else if (st.seen_class < 0 && *answer >= 0) st.seen_class = *answer;            // the first look has finished
+        else if (st.seen_class == 0 && *answer > 0) st.seen_class = *answer;            // the latest look found a raster again
+        else if (st.seen_class > 0 && st.feedback_armed) {
+            // the launches reported since the last look
+            const int now_mixed = fb[0], now_launches = fb[1];
+            const int mixed = now_mixed - st.feedback_mixed, launches = now_launches - st.feedback_launches;
+            st.feedback_mixed = now_mixed; st.feedback_launches = now_launches;
+            const int tiles = (num_rays + 31) / 32;
+            if (launches > 0 && (long long)mixed * 4 > (long long)launches * tiles) {     // most warps mixed: not camera rays any more
+                st.seen_class = 0;
+                st.feedback_armed = false;
+                *answer = 0;
+            }
+        }
+        if (!same || st.seen_class == 0) {
+            *answer = -1;
             int* host_alias = nullptr;
             HGB_CUDA(cudaHostGetDevicePointer(&host_alias, st.layout_host, 0));
             detect_raster<<<1, 256>>>(rays, num_rays, st.layout, host_alias); count_launch();
             st.seen_rays = rays;
             st.seen_count = num_rays;
         }
-        if (variant == 3) variant = *static_cast<volatile int*>(st.layout_host) == 0 ? 1 : 4;
+        if (variant == 3) variant = st.seen_class == 0 ? 1 : 4;
+        if (variant == 4 && st.seen_class > 0) {
+            feedback = st.feedback_dev;
+            if (!st.feedback_armed) {
+                // fresh baseline: counters restart from zero for this buffer
+                HGB_CUDA(cudaMemsetAsync(st.feedback_dev, 0, 2 * sizeof(int), 0));
+                st.feedback_host[0] = st.feedback_host[1] = 0;
+                st.feedback_mixed = 0; st.feedback_launches = 0; st.feedback_armed = true; st.feedback_tick = 0;
+            }
+        }
     }
     enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, (variant == 2 || variant == 4) ? st.layout : nullptr, 0,
-                            st.counter, st.num_sms, 0);
+                            st.counter, st.num_sms, 0, feedback);
+    if (feedback) {
+        // copied back after launches 1, 2, 4 and then every 8th: one 8-byte copy in eight launches
+        const int tick = ++st.feedback_tick;
+        if (tick <= 2 || (tick & 3) == 0 && (tick == 4 || (tick & 7) == 0))
+            HGB_CUDA(cudaMemcpyAsync(st.feedback_host, st.feedback_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, 0));
+    }
     HGB_CUDA(cudaGetLastError());
 }
 
@@ -779,7 +839,14 @@ int host_raster_width(const Ray* rays, int n) {
     if (width >= limit || width < 64 || width % kTileW != 0 || n % width != 0 || (n / width) % kTileH != 0) return 0;
     for (int k = 0; k < 62; k++)
         if (!continues(width + 1 + k) || !continues(n - width + 1 + k)) return 0;
-    return width;
+    constexpr int kSpot = 1024;                      // same spot check as detect_raster
+    int misses = 0;
+    for (int k = 0; k < kSpot; k++) {
+        int i = int((long long)n * k / kSpot) + 1 + (k * 37) % 61;
+        if (i >= n) i = n - 1;
+        if (i % width != 0 && !continues(i)) misses++;
+    }
+    return misses > kSpot / 16 ? 0 : width;
 }
 
 template <typename CellT, bool kPrimId>

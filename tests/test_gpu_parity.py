@@ -454,6 +454,31 @@ def test_host_frames_are_pipelined_without_changing_hits(lib, sponza, pinned):
             assert np.array_equal(got["id"], ref["id"]) and np.array_equal(got["t"].view(np.uint32), ref["t"].view(np.uint32))
 
 
+def test_a_reused_ray_buffer_may_change_its_character(lib, sponza):
+    """The library remembers what kind of buffer it saw at an address (raster of camera rays or incoherent) and
+    re-classifies it from kernel feedback when the contents change. Whatever it believes, the hits are the same."""
+    tris, sc, _ = sponza
+    sc.setup_traversal()
+    raster = scenes.default_view(tris, 640, 360)
+    n = raster.shape[0]
+    first = sc.trace(raster, HIT_PRIM_ID)
+    waves = [raster, scenes.bounce_rays(tris, raster, first["id"], first["t"]), scenes.random_rays(tris, n, seed=3), raster]
+    lib.set_option("traverse_variant", 0)
+    want = [sc.trace(w, HIT_PRIM_ID) for w in waves]
+    lib.set_option("traverse_variant", 3)
+    d_rays, d_hits = sc.device_alloc(n * 32), sc.device_alloc(n * 16)
+    try:
+        for _ in range(2):
+            for w, expect in zip(waves, want):
+                sc.to_device(d_rays, w)
+                for _ in range(12):                       # long enough for the feedback to arrive and the policy to flip
+                    sc.traverse(d_rays, d_hits, n, HIT_PRIM_ID)
+                    got = sc.to_host(np.empty(n, dtype=expect.dtype), d_hits)
+                    assert np.array_equal(got["id"], expect["id"]) and np.array_equal(got["t"].view(np.uint32), expect["t"].view(np.uint32))
+    finally:
+        sc.device_free(d_rays); sc.device_free(d_hits)
+
+
 def test_tracing_a_grid_without_its_setup_is_an_error(lib):
     """The traversal constants are per process (src/traverse.cu:7-12); the C ABI refuses to walk a grid
     with another grid's constants instead of letting the kernel run wild."""
