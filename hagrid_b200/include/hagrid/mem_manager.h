@@ -2,10 +2,11 @@
 // (same public interface and object layout as src/mem_manager.h:21-119, so
 // a front end compiled against either header links against this library).
 //
-// Slots are recycled best-fit: alloc() picks the free slot whose capacity is
-// closest to the request and grows it only when too small. In `keep` mode
-// freed slots retain their memory (= --keep-alive, fast rebuilds); otherwise
-// free() returns the memory. B200-first difference: slot memory comes from
+// Slots are recycled best-fit: alloc() picks the smallest idle slot that is large
+// enough and grows the largest idle one (with some slack) when none is. In `keep`
+// mode freed slots retain their memory (= --keep-alive, fast rebuilds) and are
+// never given back while the manager lives — a B200 has 180 GB; otherwise free()
+// returns the memory. B200-first difference: slot memory comes from
 // the device's stream-ordered pool (cudaMallocAsync on the legacy default
 // stream with an unlimited release threshold), so grow/shrink never forces a
 // device-wide synchronisation the way cudaMalloc/cudaFree do.
@@ -42,14 +43,18 @@ public:
     template <typename T>
     HOST T* alloc(size_t n) {
         const size_t bytes = n * sizeof(T);
-        int best = -1;
-        size_t best_gap = std::numeric_limits<size_t>::max();
+        // smallest idle slot that already holds `bytes`; failing that the largest idle one (it is grown).
+        // Capacities only ever grow, so a repeated build finds every buffer it needs after a few rounds and
+        // stops talking to the driver (the reference picks the slot of closest size, src/mem_manager.h:46-70,
+        // which keeps re-growing slots that were a little too small).
+        int best = -1, largest = -1;
         for (size_t i = 0; i < slots_.size(); i++) {
             if (slots_[i].in_use) continue;
             const size_t have = slots_[i].size;
-            const size_t gap = have > bytes ? have - bytes : bytes - have;
-            if (gap < best_gap) { best_gap = gap; best = int(i); }
+            if (have >= bytes && (best < 0 || have < slots_[best].size)) best = int(i);
+            if (largest < 0 || have > slots_[largest].size) largest = int(i);
         }
+        if (best < 0) best = largest;
         if (best < 0) {
             best = int(slots_.size());
             slots_.emplace_back();
