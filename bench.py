@@ -14,8 +14,8 @@ flushed between steps. Mrays/s = rays * K / (1000 * sum ms), max over ranks.
   e2e    the same frame through the C ABI with HOST buffers: pinned H2D of the rays,
          traversal, D2H of the hits, all inside the timed region
 N > 1 (torchrun): one process per GPU, every rank builds its replica of the grid and
-traces its own frame of an N-view camera path (weak scaling, no data-path collective;
-one all-reduce of three counters per measurement).
+traces the same frame (weak scaling with equal work per GPU, no data-path collective;
+one all-reduce of the timing counters per measurement).
 
 --impl reference runs cg-saarland/hagrid itself: the reference has no CPU path, so
 its CUDA sources rebuilt for sm_100a (oracle/_ref, see oracle/build_ref.sh) are driven
@@ -158,7 +158,7 @@ def main():
 
     lib = Library(ref_lib_path) if reference else Library()
     tris = scenes.sponza262k()
-    rays = camera_path_view(tris, scenes, rank)
+    rays = camera_path_view(tris, scenes, 0)      # weak scaling: the same frame on every rank, so per-GPU work does not depend on N
     n = rays.shape[0]
 
     # ---- construction (every rank builds its own replica; reported, not the headline)
@@ -277,7 +277,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": args.impl,
             "config": {"workload": "C2: sponza262k stand-in (262267 tris), 1920x1080 primary rays, -td 0.15 -sd 3.0 -a 0.995 -e 3",
-                       "rays_per_step_per_gpu": n, "frames": "rank r traces view r of an N-view camera path; grid replicated",
+                       "rays_per_step_per_gpu": n, "frames": "every rank builds its own replica of the grid and traces the same 1920x1080 frame (fixed work per GPU)",
                        "grid": {k: info[k] for k in ("dims", "shift", "num_cells", "num_entries", "num_refs")},
                        "l2": "256 MiB memset between steps (L2 flushed); scene+rays+hits = %.1f MB" % (algo_bytes / 1e6),
                        "timing": "CUDA event pair per step on the legacy default stream, sum over steps, max over ranks"},
