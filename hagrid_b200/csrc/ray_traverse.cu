@@ -517,7 +517,7 @@ constexpr int kBlockThreads = 128;
 // ---------------------------------------------------------------------------
 // Kernel B: persistent warps with majority scheduling (incoherent buffers). Every iteration the warp
 // counts the lanes that need a cell step and the lanes that own references and serves the larger
-// group (tools/warp_sim.py, policy "count": 0.31 cell + 0.34 triangle iterations per ray against
+// group (offline SIMT model, DESIGN.md section 4.1, policy "count": 0.31 cell + 0.34 triangle iterations per ray against
 // 0.86 + 0.29 when the cell phase runs until every lane owns references). With fewer instructions the
 // kernel is bound by the latency of its dependent loads, the ray-counter atomic first among them (ncu:
 // 13 % of the stall samples), so rays are reserved 32 at a time two blocks ahead: the atomic of a block

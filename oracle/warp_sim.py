@@ -1,4 +1,5 @@
-"""Offline SIMT model (CPU, oracle only): warp-level iteration counts of scheduling strategies for the
+"""TEST/ANALYSIS INFRASTRUCTURE (uses the CPU oracle; nothing in the product imports it).
+Offline SIMT model (CPU, oracle only): warp-level iteration counts of scheduling strategies for the
 traversal loop, from the per-ray sequences of (cell visit, #references) the oracle records.
   if-while   : every iteration = one cell step for all live lanes, then a triangle loop of max(count) trips
   while-while: lanes step until they own a non-empty cell (or die), then one triangle loop

@@ -61,3 +61,16 @@ def test_struct_layouts():
     assert api.CELL_DTYPE.itemsize == 32 and api.SMALL_CELL_DTYPE.itemsize == 16
     assert api.CELL_DTYPE.fields["begin"][1] == 12 and api.CELL_DTYPE.fields["max"][1] == 16
     assert api.SMALL_CELL_DTYPE.fields["max"][1] == 6 and api.SMALL_CELL_DTYPE.fields["begin"][1] == 12
+
+
+def test_missing_library_is_a_loud_error(tmp_path):
+    from hagrid_b200 import HagridError, Library
+    with pytest.raises(HagridError, match="no CPU fallback"):
+        Library(tmp_path / "libhagrid_b200.so")
+
+
+def test_only_tests_bench_and_smoke_use_the_oracle():
+    """oracle/ is test infrastructure: nothing outside tests/, bench.py and __graft_entry__.py imports it."""
+    for path in list((ROOT / "hagrid_b200").rglob("*.py")) + list((ROOT / "tools").glob("*.py")):
+        text = path.read_text()
+        assert "from oracle" not in text and "import oracle" not in text, path
