@@ -115,6 +115,56 @@ __global__ void __launch_bounds__(kBlock) grow_cells(const __grid_constant__ Exp
     dev::store_cell(out_cells, id, c.min_x, c.min_y, c.min_z, c.begin, c.max_x, c.max_y, c.max_z, c.end);
 }
 
+/// The same step with two lanes per cell, one per face of the axis. The two face scans are independent (both
+/// start from the same box) and the scan of a large face is a long chain of dependent voxel-map look-ups, so
+/// splitting them halves the critical path of the heavy cells that decide the kernel's duration. Pays off while
+/// the kernel is latency-bound (C2, 234 K cells: -9 %); with millions of cells it is bandwidth-bound and the
+/// doubled cell loads cost more than the shorter chains save (C4, 7.1 M cells: +49 %), so expand_grid() picks.
+template <int axis>
+__global__ void __launch_bounds__(kBlock) grow_cells_paired(const __grid_constant__ ExpandParams P, const uint32_t* __restrict__ entries,
+                                                            const int* __restrict__ refs, const Cell* __restrict__ cells,
+                                                            Cell* __restrict__ out_cells, int* __restrict__ flags, int num_cells) {
+    constexpr unsigned kAll = 0xFFFFFFFFu;
+    const int thread = blockIdx.x * kBlock + threadIdx.x;
+    const int id = thread >> 1;
+    const bool high_face = thread & 1;
+    int flag = 0;
+    bool active = false;
+    if (id < num_cells) {
+        flag = flags[id];
+        active = (flag & (1 << axis)) != 0;
+    }
+    dev::CellBox c = {};
+    bool keep_going = false;
+    int growth = 0;
+    if (active) {
+        c = dev::load_cell_box(cells, id);
+        growth = high_face ? face_growth<axis, true>(P, entries, refs, cells, c, keep_going)
+                           : face_growth<axis, false>(P, entries, refs, cells, c, keep_going);
+    }
+    // the low-face lane (even) collects the high-face lane's result and writes the cell
+    const int other_growth = __shfl_xor_sync(kAll, growth, 1);
+    const bool other_keep = __shfl_xor_sync(kAll, int(keep_going), 1) != 0;
+    if (!active || high_face) return;
+    const int low = growth, high = other_growth;
+    keep_going |= other_keep;
+    if (axis == 0) { c.min_x += low; c.max_x += high; }
+    if (axis == 1) { c.min_y += low; c.max_y += high; }
+    if (axis == 2) { c.min_z += low; c.max_z += high; }
+    flags[id] = (keep_going ? 1 << axis : 0) | (flag & ~(1 << axis));
+    dev::store_cell(out_cells, id, c.min_x, c.min_y, c.min_z, c.begin, c.max_x, c.max_y, c.max_z, c.end);
+}
+
+template <int axis>
+void grow_step(const ExpandParams& P, const uint32_t* entries, const Grid& grid, Cell* out, int* flags) {
+    constexpr int kPairedBelow = 1 << 20;
+    if (grid.num_cells < kPairedBelow)
+        grow_cells_paired<axis><<<(2 * grid.num_cells + kBlock - 1) / kBlock, kBlock>>>(P, entries, grid.ref_ids, grid.cells, out, flags, grid.num_cells);
+    else
+        grow_cells<axis><<<(grid.num_cells + kBlock - 1) / kBlock, kBlock>>>(P, entries, grid.ref_ids, grid.cells, out, flags, grid.num_cells);
+    count_launch();
+}
+
 } // namespace
 
 void expand_grid(MemManager& mem, Grid& grid, const Tri*, int iters) {
@@ -130,13 +180,12 @@ void expand_grid(MemManager& mem, Grid& grid, const Tri*, int iters) {
     P.shift = grid.shift;
 
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
-    const int blocks = (grid.num_cells + kBlock - 1) / kBlock;
     for (int i = 0; i < iters && grid.num_cells > 0; i++) {
-        grow_cells<0><<<blocks, kBlock>>>(P, entries, grid.ref_ids, grid.cells, other, flags, grid.num_cells); count_launch();
+        grow_step<0>(P, entries, grid, other, flags);
         std::swap(other, grid.cells);
-        grow_cells<1><<<blocks, kBlock>>>(P, entries, grid.ref_ids, grid.cells, other, flags, grid.num_cells); count_launch();
+        grow_step<1>(P, entries, grid, other, flags);
         std::swap(other, grid.cells);
-        grow_cells<2><<<blocks, kBlock>>>(P, entries, grid.ref_ids, grid.cells, other, flags, grid.num_cells); count_launch();
+        grow_step<2>(P, entries, grid, other, flags);
         std::swap(other, grid.cells);
     }
     HGB_CUDA(cudaGetLastError());
