@@ -3,8 +3,8 @@
 // levels are fused into one dense (2^d)^3 voxel-map node, d = min(subtree depth, 3).
 //
 // Differences in execution, not in result: collapse and subtree depth are one
-// kernel per level (bottom-up); the dense nodes are written by warps that first
-// compact the inner entries of 32 consecutive source entries with __ballot_sync
+// kernel per level (bottom-up); the dense nodes are written one thread per output
+// word, each finding its source entry by binary search in the scanned node sizes
 // (the reference launches one 64-thread block per source entry, most of which
 // exit immediately); one host synchronisation per group of three levels.
 #include <algorithm>
@@ -66,43 +66,41 @@ __global__ void __launch_bounds__(kBlock) copy_top(const uint32_t* __restrict__ 
     out[id] = e;
 }
 
-/// Dense nodes of one group of levels (flatten_level, src/flatten.cu:65-107).
-/// Sub-entry i is read as d octal digits, most significant first; each digit picks a
-/// child while the walk is still on an inner word, and sets one bit of x, y, z.
-__global__ void __launch_bounds__(kBlock) write_nodes(const uint32_t* __restrict__ entries, const int* __restrict__ node_start,
-                                                      const int* __restrict__ depths, uint32_t* __restrict__ out,
-                                                      int first, int offset, int next_offset, int count) {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
-    const int base = warp * 32;
-    if (base >= count) return;
-    const int mine = base + lane;
-    const int my_depth = mine < count ? min(depths[first + mine], kFlatLevels) : 0;
-    unsigned todo = __ballot_sync(kAll, my_depth > 0);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int id = first + base + src;
-        const int d = __shfl_sync(kAll, my_depth, src);
-        const int start = offset + node_start[id];
-        const uint32_t root = entries[id];
-        for (int i = lane; i < (1 << (3 * d)); i += 32) {
-            uint32_t e = root;
-            int x = 0, y = 0, z = 0, at = id;
-            for (int level = d - 1; level >= 0; level--) {
-                const int digit = (i >> (3 * level)) & 7;
-                x |= (digit & 1) << level;
-                y |= ((digit >> 1) & 1) << level;
-                z |= (digit >> 2) << level;
-                if (e & 3u) {
-                    at = int(e >> 2) + digit;
-                    e = entries[at];
-                }
-            }
-            if (e & 3u) e = (uint32_t(next_offset + node_start[at]) << 2) | uint32_t(min(depths[at], kFlatLevels));
-            out[start + x + ((y + (z << d)) << d)] = e;
+/// Dense nodes of one group of levels (flatten_level, src/flatten.cu:65-107): sub-entry i of a node is read as d
+/// octal digits, most significant first; each digit picks a child while the walk is still on an inner word, and
+/// sets one bit of x, y, z.
+/// One thread per OUTPUT word: the thread finds the source entry whose node contains its word by
+/// a binary search in the exclusive scan of the node sizes (the last entry that starts at or before the word;
+/// leaves have size 0 and share their successor's start), then walks the d digits. Every thread has the same
+/// amount of work, whereas a block (the reference) or a warp per group of source entries writes anything
+/// between nothing and 16 384 words.
+__global__ void __launch_bounds__(kBlock) write_nodes_by_word(const uint32_t* __restrict__ entries, const int* __restrict__ node_start,
+                                                              const int* __restrict__ depths, uint32_t* __restrict__ out,
+                                                              int first, int offset, int next_offset, int count, int total_words) {
+    const int word = blockIdx.x * kBlock + threadIdx.x;
+    if (word >= total_words) return;
+    int lo = 0, hi = count;                                   // first index whose start exceeds `word`
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(node_start + first + mid) > word) hi = mid; else lo = mid + 1;
+    }
+    const int id = first + lo - 1;
+    const int i = word - __ldg(node_start + id);
+    const int d = min(__ldg(depths + id), kFlatLevels);
+    uint32_t e = __ldg(entries + id);
+    int x = 0, y = 0, z = 0, at = id;
+    for (int level = d - 1; level >= 0; level--) {
+        const int digit = (i >> (3 * level)) & 7;
+        x |= (digit & 1) << level;
+        y |= ((digit >> 1) & 1) << level;
+        z |= (digit >> 2) << level;
+        if (e & 3u) {
+            at = int(e >> 2) + digit;
+            e = __ldg(entries + at);
         }
     }
+    if (e & 3u) e = (uint32_t(next_offset + __ldg(node_start + at)) << 2) | uint32_t(min(__ldg(depths + at), kFlatLevels));
+    out[offset + (word - i) + x + ((y + (z << d)) << d)] = e;
 }
 
 inline int blocks_for(int n) { return (n + kBlock - 1) / kBlock; }
@@ -123,7 +121,7 @@ void flatten_grid(MemManager& mem, Grid& grid) {
     int* node_start = mem.alloc<int>(size_t(grid.num_entries) + 1);
     int* scan_tmp = mem.alloc<int>(prim::num_tiles(grid.num_entries) + 2);
     int* total_dev = scan_tmp + prim::num_tiles(grid.num_entries) + 1;
-    std::vector<int> group_offset(std::max(grid.shift, 1), 0);
+    std::vector<int> group_offset(std::max(grid.shift, 1), 0), group_words(std::max(grid.shift, 1), 0);
     int total_entries = grid.offsets[0];
     for (int level = 0; level < grid.shift; level += kFlatLevels) {
         const int first = level > 0 ? grid.offsets[level - 1] : 0;
@@ -132,6 +130,7 @@ void flatten_grid(MemManager& mem, Grid& grid) {
         int group_entries = 0;
         HGB_CUDA(cudaMemcpy(&group_entries, total_dev, sizeof(int), cudaMemcpyDeviceToHost));
         group_offset[level] = total_entries;
+        group_words[level] = group_entries;
         total_entries += group_entries;
     }
 
@@ -142,8 +141,9 @@ void flatten_grid(MemManager& mem, Grid& grid) {
         const int first = level > 0 ? grid.offsets[level - 1] : 0;
         const int count = grid.offsets[level] - first;
         const int next_offset = level + kFlatLevels < grid.shift ? group_offset[level + kFlatLevels] : 0;
-        if (count > 0)
-            write_nodes<<<blocks_for(count), kBlock>>>(entries, node_start, depths, out, first, group_offset[level], next_offset, count); count_launch();
+        if (count > 0 && group_words[level] > 0)
+            write_nodes_by_word<<<blocks_for(group_words[level]), kBlock>>>(entries, node_start, depths, out, first, group_offset[level],
+                                                                           next_offset, count, group_words[level]); count_launch();
         new_offsets.push_back(group_offset[level]);
     }
     new_offsets.push_back(total_entries);
