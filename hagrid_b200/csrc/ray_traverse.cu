@@ -749,8 +749,8 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
     int variant = traverse_variant();
     int* feedback = nullptr;
     if (variant >= 2 && variant <= 4) {
-        // What kind of buffer is this? A new one (other address or size) is looked at on the device,
-        // asynchronously: this launch reads the answer from device memory, later launches know it on the host.
+        // What kind of buffer is this? A new one (other address or size) is looked at on the device before its
+        // first launch; the answer is remembered on the host.
         // A buffer known as a raster is not looked at again — the tile kernel reports when its contents stop
         // behaving like one (feedback words) — and a buffer known as incoherent is looked at before every
         // launch (a 10 us kernel in front of one that takes several hundred): callers reuse ray buffers.
@@ -777,6 +777,12 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
             int* host_alias = nullptr;
             HGB_CUDA(cudaHostGetDevicePointer(&host_alias, st.layout_host, 0));
             detect_raster<<<1, 256>>>(rays, num_rays, st.layout, host_alias); count_launch();
+            if (!same) {
+                // a buffer never seen before: wait for the answer (about 10 us, once per buffer) instead of
+                // tracing its first frame with a kernel that may be the wrong one by a factor of 1.7
+                HGB_CUDA(cudaStreamSynchronize(0));
+                st.seen_class = *answer;
+            }
             st.seen_rays = rays;
             st.seen_count = num_rays;
         }

@@ -9,7 +9,8 @@ namespace hagrid {
 /// Captures the grid constants used by traverse_grid (once per grid).
 void setup_traversal(const Grid& grid);
 
-/// Closest hit of every ray; asynchronous on the legacy default stream.
+/// Closest hit of every ray; asynchronous on the legacy default stream (the first call for a ray buffer not seen
+/// before waits about 10 us for a look at its layout: camera raster or incoherent).
 /// Reference-verbatim result: Hit::id holds the traversal step count
 /// (src/traverse.cu:80,93), Hit::t the hit distance (ray.tmax if none).
 void traverse_grid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays);
