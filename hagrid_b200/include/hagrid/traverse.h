@@ -1,53 +1,6 @@
-// Traversal API — src/traverse.h:11-14 plus one extra entry point.
+// Compatibility name: the reference's front end includes "traverse.h" (src/traverse.h); the traversal entry
+// points of this library are declared in hgb_api.h.
 #ifndef TRAVERSE_H
 #define TRAVERSE_H
-
-#include "hgb_types.h"
-
-namespace hagrid {
-
-/// Captures the grid constants used by traverse_grid (once per grid).
-void setup_traversal(const Grid& grid);
-
-/// Closest hit of every ray; asynchronous on the legacy default stream (the first call for a ray buffer not seen
-/// before waits about 10 us for a look at its layout: camera raster or incoherent).
-/// Reference-verbatim result: Hit::id holds the traversal step count
-/// (src/traverse.cu:80,93), Hit::t the hit distance (ray.tmax if none).
-void traverse_grid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays);
-
-/// Same traversal, but Hit::id is the primitive index (-1 = no hit) as
-/// documented in src/ray.h:22. Not part of the reference API.
-void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays);
-
-/// One interactive frame with HOST buffers (the loop body of src/main.cpp:599-613): uploads the rays,
-/// traces them, downloads the hits; returns when `host_hits` is complete. Upload, traversal and download
-/// are pipelined in chunks over several streams (fastest with page-locked host buffers; pageable ones
-/// work). `dev_rays`/`dev_hits` are device staging buffers of `num_rays` elements owned by the caller.
-/// Not part of the reference API.
-void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays, Hit* host_hits, int num_rays,
-                        Ray* dev_rays, Hit* dev_hits, bool prim_ids);
-
-/// Camera of a frame: what gen_camera of the reference's front end produces (src/main.cpp:18-23,42-50).
-struct FrameCamera { vec3 eye, right, up, dir; };
-
-/// gen_camera (src/main.cpp:42-50), host arithmetic.
-FrameCamera make_camera(const vec3& eye, const vec3& center, const vec3& up, float fov, float ratio);
-
-/// gen_rays (src/main.cpp:52-66) on the device: width x height rays in scan-line order into the device
-/// buffer `rays`, bit-identical to the host loop. Asynchronous on the legacy default stream.
-void generate_rays(const FrameCamera& cam, float clip, int width, int height, Ray* rays);
-
-/// One frame of the reference's viewer (src/main.cpp:591-625) fused into one launch: primary rays are
-/// generated, traced and coloured on the device; `pixels` (device, width * height BGRA words) receives
-/// what update_surface (src/main.cpp:90-111) would write: mode 0 = depth, 1 = step count as grey,
-/// 2 = step count as heat map. Asynchronous on the legacy default stream. Not part of the reference API.
-void render_frame(const Grid& grid, const Tri* tris, const FrameCamera& cam, float clip, int width, int height,
-                  int mode, unsigned* pixels);
-
-/// Tuning switches: "traverse_variant" (0 = one thread per ray, 1 = persistent phase-scheduled warps,
-/// 2 = one thread per ray re-tiled 8x4 on rasters, 4 = resident warps pulling 8x4 tiles, 3 = automatic) and
-/// "host_frame_chunk_rays" (chunk size of traverse_grid_host). Returns false for unknown keys.
-bool set_traversal_option(const char* key, int value);
-
-} // namespace hagrid
+#include "hgb_api.h"
 #endif
