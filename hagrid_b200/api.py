@@ -80,6 +80,9 @@ _SIGNATURES = {
     "hgb_make_camera": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
     "hgb_generate_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "hgb_render_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hgb_generate_bounce_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_uint,
+                                          C.c_void_p]),
+    "hgb_save_image": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "hgb_rays_file_count": (C.c_longlong, [C.c_char_p]),
     "hgb_load_rays": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_float, C.c_float, C.c_void_p]),
     "hgb_save_rays": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
@@ -144,6 +147,14 @@ def make_camera(eye, center, up, fov: float, ratio: float, lib: "Library | None"
     cam = np.empty(12, dtype="<f4")
     lib.check(lib.dll.hgb_make_camera(_ptr(e), _ptr(c), _ptr(u), fov, ratio, _ptr(cam)), "make_camera")
     return cam
+
+
+def save_image(path, bgra: np.ndarray, lib: "Library | None" = None):
+    """A frame as returned by Scene.render_frame ((height, width, 4) BGRA bytes) to a binary PPM file."""
+    lib = lib or library()
+    bgra = np.ascontiguousarray(bgra, dtype=np.uint8)
+    assert bgra.ndim == 3 and bgra.shape[2] == 4
+    lib.check(lib.dll.hgb_save_image(str(path).encode(), _ptr(bgra), bgra.shape[1], bgra.shape[0]), "save_image")
 
 
 def parse_obj(path, threads: int = 0, lib: "Library | None" = None):
@@ -286,6 +297,28 @@ class Scene:
             out = np.empty((height, width, 4), dtype=np.uint8)
         self.lib.check(self.lib.dll.hgb_render_frame(self._h, _ptr(cam), clip, width, height, mode, _ptr(out)), "render_frame")
         return out
+
+    def bounce_rays_device(self, dev_rays: int, dev_hits: int, num_rays: int, offset: float, tmax: float, seed: int,
+                           dev_out: int | None = None):
+        """Second wave on the device (hgb_generate_bounce_rays): hits stay in HBM; in place when `dev_out` is None."""
+        self.lib.check(self.lib.dll.hgb_generate_bounce_rays(self._h, dev_rays, dev_hits, num_rays, offset, tmax,
+                                                             seed & 0xFFFFFFFF, dev_out if dev_out else dev_rays),
+                       "generate_bounce_rays")
+
+    def bounce_rays(self, rays: np.ndarray, hits: np.ndarray, offset: float, tmax: float, seed: int) -> np.ndarray:
+        """Host-array convenience over bounce_rays_device: `hits` are primitive-id hits of `rays`."""
+        rays = np.ascontiguousarray(rays); hits = np.ascontiguousarray(hits)
+        assert rays.dtype == RAY_DTYPE and hits.dtype == HIT_DTYPE and rays.shape[0] == hits.shape[0]
+        n = rays.shape[0]
+        if n == 0:
+            return rays.copy()
+        d_rays, d_hits = self.device_alloc(n * 32), self.device_alloc(n * 16)
+        try:
+            self.to_device(d_rays, rays); self.to_device(d_hits, hits)
+            self.bounce_rays_device(d_rays, d_hits, n, offset, tmax, seed)
+            return self.to_host(np.empty(n, dtype=RAY_DTYPE), d_rays)
+        finally:
+            self.device_free(d_rays); self.device_free(d_hits)
 
     # --- on-disk formats ------------------------------------------------------------
     def load_rays(self, path, tmin: float = 0.0, tmax: float = float(np.finfo(np.float32).max)) -> np.ndarray:

@@ -407,6 +407,20 @@ int hgb_generate_rays(hgb_scene* s, const float cam[12], float clip, int width, 
     return 0;
 }
 
+int hgb_generate_bounce_rays(hgb_scene* s, const void* dev_rays, const void* dev_hits, int num_rays, float offset,
+                             float tmax, unsigned seed, void* dev_out) {
+    if (!bind(s)) return -1;
+    if (num_rays < 0 || (num_rays > 0 && (!dev_rays || !dev_hits || !dev_out))) return fail("generate_bounce_rays: bad argument");
+    if (!s->tris) return fail("generate_bounce_rays: the scene has no triangles");
+#ifdef HGB_REFERENCE_BUILD
+    return fail("generate_bounce_rays: the reference has no second-wave ray generation");
+#else
+    generate_bounce_rays(s->tris, s->num_tris, static_cast<const Ray*>(dev_rays), static_cast<const Hit*>(dev_hits),
+                         num_rays, offset, tmax, seed, static_cast<Ray*>(dev_out));
+    return 0;
+#endif
+}
+
 int hgb_render_frame(hgb_scene* s, const float cam[12], float clip, int width, int height, int display_mode, void* host_bgra) {
     if (!bind(s)) return -1;
     if (!s->grid.entries) return fail("render_frame: no grid");
@@ -469,6 +483,15 @@ int hgb_save_rays(hgb_scene* s, const char* path, const void* dev_rays, long lon
     return fail("save_rays: the reference has no ray file writer");
 #else
     return save_rays_from_device(s->mem, path, static_cast<const Ray*>(dev_rays), count) ? 0 : fail("save_rays: cannot write file");
+#endif
+}
+
+int hgb_save_image(const char* path, const void* host_bgra, int width, int height) {
+    if (!path || !host_bgra || width <= 0 || height <= 0) return fail("save_image: bad argument");
+#ifdef HGB_REFERENCE_BUILD
+    return fail("save_image: the reference only draws into an SDL window");
+#else
+    return save_image_ppm(path, static_cast<const unsigned char*>(host_bgra), width, height) ? 0 : fail("save_image: cannot write file");
 #endif
 }
 

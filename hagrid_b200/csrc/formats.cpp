@@ -91,6 +91,20 @@ bool save_rays_from_device(MemManager& mem, const std::string& path, const Ray* 
     return f.write(host.data(), host.size() * sizeof(float));
 }
 
+bool save_image_ppm(const std::string& path, const unsigned char* bgra, int width, int height) {
+    File f(path, "wb");
+    if (!f.fp) return false;
+    char head[64];
+    const int len = std::snprintf(head, sizeof(head), "P6\n%d %d\n255\n", width, height);
+    std::vector<unsigned char> rgb(size_t(width) * height * 3);
+    for (size_t i = 0; i < size_t(width) * height; i++) {
+        rgb[3 * i + 0] = bgra[4 * i + 2];
+        rgb[3 * i + 1] = bgra[4 * i + 1];
+        rgb[3 * i + 2] = bgra[4 * i + 0];
+    }
+    return f.write(head, size_t(len)) && f.write(rgb.data(), rgb.size());
+}
+
 bool save_grid(MemManager& mem, const std::string& path, const Grid& grid, std::string& error) {
     if (!grid.entries || (!grid.cells && !grid.small_cells)) { error = "no grid to save"; return false; }
     File f(path, "wb");

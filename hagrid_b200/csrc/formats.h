@@ -24,6 +24,10 @@ long long load_rays_to_device(MemManager& mem, const std::string& path, float tm
 /// Writes rays (device) as a .rays file (org and dir only, like the reference's format).
 bool save_rays_from_device(MemManager& mem, const std::string& path, const Ray* rays, long long count);
 
+/// Headless stand-in for the SDL window of the reference's viewer (src/main.cpp:558-625): writes a frame of
+/// BGRA words (what update_surface / render_frame produce) as a binary PPM (P6, RGB).
+bool save_image_ppm(const std::string& path, const unsigned char* bgra, int width, int height);
+
 bool save_grid(MemManager& mem, const std::string& path, const Grid& grid, std::string& error);
 /// Arrays come from `mem` like those of build_grid; `grid`'s previous arrays must have been freed by the caller.
 bool load_grid(MemManager& mem, const std::string& path, Grid& grid, std::string& error);

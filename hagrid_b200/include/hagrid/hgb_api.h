@@ -47,6 +47,15 @@ FrameCamera make_camera(const vec3& eye, const vec3& center, const vec3& up, flo
 /// buffer `rays`, bit-identical to the host loop. Asynchronous on the legacy default stream.
 void generate_rays(const FrameCamera& cam, float clip, int width, int height, Ray* rays);
 
+/// Second wave (BASELINE config C5; the reference stops at primary rays): for every ray whose `hits[i].id`
+/// names a triangle (hits from traverse_grid_prim_ids) emit a cosine-weighted diffuse bounce -- origin =
+/// hit point + `offset` x unit normal facing the ray, direction from a counter-based generator keyed by
+/// (`seed`, i), tmin 0, tmax `tmax`; rays that missed are emitted again unchanged. `out` may be `rays`.
+/// IEEE arithmetic only: oracle/hagrid_oracle.c og_bounce_rays produces the same bits on the CPU.
+/// Asynchronous on the legacy default stream. Not part of the reference API.
+void generate_bounce_rays(const Tri* tris, int num_tris, const Ray* rays, const Hit* hits, int num_rays,
+                          float offset, float tmax, unsigned seed, Ray* out);
+
 /// One frame of the reference's viewer (src/main.cpp:591-625) fused into one launch: primary rays are
 /// generated, traced and coloured on the device; `pixels` (device, width * height BGRA words) receives
 /// what update_surface (src/main.cpp:90-111) would write: mode 0 = depth, 1 = step count as grey,

@@ -156,6 +156,20 @@ HGB_API int  hgb_generate_rays(hgb_scene* scene, const float cam[12], float clip
 HGB_API int  hgb_render_frame(hgb_scene* scene, const float cam[12], float clip, int width, int height,
                               int display_mode, void* host_bgra);
 
+/* Second wave of BASELINE.json's config C5. The reference's front end stops at primary rays
+ * (gen_rays, src/main.cpp:52-66); this entry point defines the next stage on the device so that the hits never
+ * leave HBM between the two waves: ray i with a primitive-id hit (HGB_HIT_PRIM_ID) becomes a cosine-weighted
+ * diffuse bounce (origin = hit point + offset x unit normal turned towards the ray, tmin 0, tmax `tmax`,
+ * direction from a counter-based generator keyed by (seed, i)); a ray that missed is emitted again unchanged.
+ * `dev_out` may equal `dev_rays`. IEEE arithmetic only; oracle/hagrid_oracle.c (og_bounce_rays) gives the same
+ * bits on the CPU. The reference build of this ABI reports an error. */
+HGB_API int  hgb_generate_bounce_rays(hgb_scene* scene, const void* dev_rays, const void* dev_hits, int num_rays,
+                                      float offset, float tmax, unsigned seed, void* dev_out);
+
+/* Headless stand-in for the viewer's SDL window (src/main.cpp:558-625): a frame of BGRA words as written by
+ * hgb_render_frame / update_surface goes to a binary PPM file (P6). */
+HGB_API int  hgb_save_image(const char* path, const void* host_bgra, int width, int height);
+
 /* On-disk formats. `.rays` is the reference's ray file (6 float32 per ray: org, dir; tmin / tmax come from the
  * caller; load_rays, src/main.cpp:277-300). hgb_load_rays fills a DEVICE buffer of hgb_rays_file_count() rays:
  * this library uploads the 24-byte records and expands them on the device, the reference build of this ABI runs

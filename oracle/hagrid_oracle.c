@@ -884,3 +884,55 @@ void og_update_surface(int mode, const og_hit* hits, float clip, int w, int h, u
         px[3] = 255;
     }
 }
+
+/* ---- second-wave rays (config C5). The reference has no such stage (its front end stops at gen_rays,
+ * src/main.cpp:52-66): the operation is DEFINED by include/hagrid_b200.h (hgb_generate_bounce_rays) and restated
+ * here operation by operation in IEEE single precision (no fmaf, sqrtf and '/' correctly rounded), so the device
+ * kernel (hagrid_b200/csrc/ray_bounce.cu) has to match bit for bit. */
+static uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+
+static float draw24(uint32_t base, uint32_t k) { return (float)(mix32(base + k) >> 8) * 0x1p-24f; }
+
+void og_bounce_rays(const og_tri* tris, int num_tris, const og_ray* rays, const og_hit* hits, int num_rays,
+                    float offset, float tmax, uint32_t seed, og_ray* out) {
+    for (int i = 0; i < num_rays; i++) {
+        const og_ray r = rays[i];
+        const og_hit h = hits[i];
+        float n[3] = {0, 0, 0}, len = 0.0f;
+        if (h.id >= 0 && h.id < num_tris) {
+            n[0] = tris[h.id].nx; n[1] = tris[h.id].ny; n[2] = tris[h.id].nz;
+            len = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+        }
+        if (!(len > 0.0f)) { out[i] = r; continue; }
+        for (int k = 0; k < 3; k++) n[k] = n[k] / len;
+        const float facing = (n[0] * r.dir[0] + n[1] * r.dir[1]) + n[2] * r.dir[2];
+        if (facing > 0.0f) for (int k = 0; k < 3; k++) n[k] = -n[k];
+        og_ray o;
+        for (int k = 0; k < 3; k++) o.org[k] = (r.org[k] + r.dir[k] * h.t) + n[k] * offset;
+        const uint32_t base = mix32(seed ^ mix32((uint32_t)i));
+        float dx = 0.0f, dy = 0.0f, s = 0.0f;
+        for (int k = 0; k < 8; k++) {
+            const float x = 2.0f * draw24(base, 2 * k) - 1.0f;
+            const float y = 2.0f * draw24(base, 2 * k + 1) - 1.0f;
+            const float q = x * x + y * y;
+            if (q < 1.0f) { dx = x; dy = y; s = q; break; }
+        }
+        const float dz = sqrtf(1.0f - s);
+        float t1[3], t2[3];
+        if (fabsf(n[0]) > 0.9f) { t1[0] = -n[2]; t1[1] = 0.0f; t1[2] = n[0]; }
+        else                    { t1[0] = 0.0f; t1[1] = n[2]; t1[2] = -n[1]; }
+        const float tl = sqrtf((t1[0] * t1[0] + t1[1] * t1[1]) + t1[2] * t1[2]);
+        for (int k = 0; k < 3; k++) t1[k] = t1[k] / tl;
+        t2[0] = n[1] * t1[2] - n[2] * t1[1];
+        t2[1] = n[2] * t1[0] - n[0] * t1[2];
+        t2[2] = n[0] * t1[1] - n[1] * t1[0];
+        for (int k = 0; k < 3; k++) o.dir[k] = (t1[k] * dx + t2[k] * dy) + n[k] * dz;
+        o.tmin = 0.0f; o.tmax = tmax;
+        out[i] = o;
+    }
+}

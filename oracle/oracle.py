@@ -55,6 +55,8 @@ def dll():
         _dll.og_gen_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
         _dll.og_gen_rays.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
         _dll.og_update_surface.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
+        _dll.og_bounce_rays.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                        C.c_uint32, C.c_void_p]
         _dll.og_traverse_record.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _dll.og_traverse_record_cells.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return _dll
@@ -153,4 +155,14 @@ def update_surface(mode: int, hits: np.ndarray, clip: float, width: int, height:
     hits = np.ascontiguousarray(hits)
     out = np.empty((height, width, 4), dtype=np.uint8)
     dll().og_update_surface(mode, hits.ctypes.data, clip, width, height, out.ctypes.data)
+    return out
+
+
+def bounce_rays(tris: np.ndarray, rays: np.ndarray, hits: np.ndarray, offset: float, tmax: float, seed: int) -> np.ndarray:
+    """Second-wave rays as include/hagrid_b200.h defines them (hgb_generate_bounce_rays); `hits` hold primitive ids."""
+    tris = np.ascontiguousarray(tris); rays = np.ascontiguousarray(rays); hits = np.ascontiguousarray(hits)
+    assert rays.dtype == RAY_DTYPE and hits.dtype.itemsize == 16 and rays.shape[0] == hits.shape[0]
+    out = np.empty(rays.shape[0], dtype=RAY_DTYPE)
+    dll().og_bounce_rays(tris.ctypes.data, tris.shape[0], rays.ctypes.data, hits.ctypes.data, rays.shape[0],
+                         offset, tmax, seed & 0xFFFFFFFF, out.ctypes.data)
     return out
