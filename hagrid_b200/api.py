@@ -219,6 +219,14 @@ class Scene:
             raise HagridError(self.lib.dll.hgb_last_error().decode())
         self.lib.check(self.lib.dll.hgb_scene_set_tris(self._h, _ptr(tris), self.num_tris), "set_tris")
 
+    def set_tris(self, tris: np.ndarray):
+        """Replaces the scene's triangles (dynamic scenes: new geometry, then build_all again)."""
+        tris = np.ascontiguousarray(tris)
+        if tris.dtype != TRI_DTYPE:
+            tris = tris.astype("<f4", copy=False).reshape(-1, 12).view(TRI_DTYPE).reshape(-1)
+        self.num_tris = int(tris.shape[0])
+        self.lib.check(self.lib.dll.hgb_scene_set_tris(self._h, _ptr(tris), self.num_tris), "set_tris")
+
     def close(self):
         if self._h:
             self.lib.dll.hgb_scene_destroy(self._h)

@@ -253,6 +253,22 @@ def hairball(num_tris: int = 2_000_000, seed: int = SEED + 4) -> np.ndarray:
     return tris
 
 
+def animate(tris: np.ndarray, phase: float, amplitude: float = 0.01) -> np.ndarray:
+    """Dynamic-scene stand-in: every vertex sways by `amplitude` x scene diagonal (a travelling wave in x and z,
+    shared by coincident vertices so the mesh stays watertight); triangle count and order are kept."""
+    lo, hi = scene_bbox(tris)
+    diag = float(np.linalg.norm(hi - lo))
+    k = 2 * np.pi * 3 / diag
+    out = []
+    for v in tri_vertices(tris):
+        v = v.astype(np.float64)
+        w = v.copy()
+        w[:, 0] += amplitude * diag * np.sin(k * v[:, 1] + phase)
+        w[:, 2] += amplitude * diag * np.cos(k * v[:, 0] + 0.7 * phase)
+        out.append(w.astype(np.float32))
+    return make_tris(*out)
+
+
 def small_mixed(num_tris: int = 3000, seed: int = 7) -> np.ndarray:
     """Small random soup with a few huge and many tiny triangles (unit tests)."""
     rng = np.random.default_rng(seed)

@@ -115,3 +115,34 @@ def test_fused_frame_equals_the_reference_viewer_loop(lib, ref_lib):
         assert np.array_equal(got, want), mode
         assert got[..., 3].min() == 255 and (mode == 0 or got[..., :3].max() > 0)
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_dynamic_scene_rebuild_and_render_matches_the_reference(lib, ref_lib):
+    """Row f4: every frame new triangles, rebuild with the keep-alive allocator (mem_manager.h:36-42), render.
+    Same images as the reference driven through the same loop; the pool stops growing after the first lap."""
+    base = scenes.atrium(30000, seed=9)
+    poses = [scenes.animate(base, 2 * np.pi * f / 4) for f in range(4)]
+    w, h = 320, 184
+    images = {}
+    for name, L in (("ref", ref_lib), ("new", lib)):
+        sc = Scene(poses[0], keep_alive=True, lib=L)
+        peaks = []
+        for lap in range(3):
+            for k, tris in enumerate(poses):
+                sc.set_tris(tris)
+                sc.build_all(0.15, 3.0)
+                sc.setup_traversal()
+                cam, clip = view(tris, w, h, yaw=0.2 * k)
+                img = sc.render_frame(cam, clip, w, h, 2)
+                if lap == 0:
+                    images.setdefault(name, []).append(img)
+                else:
+                    assert np.array_equal(img, images[name][k])
+            peaks.append(sc.peak_bytes())
+        if name == "new":
+            assert peaks[2] == peaks[1]
+        sc.close()
+    for k in range(4):
+        assert np.array_equal(images["new"][k], images["ref"][k]), k
+    assert not np.array_equal(images["new"][0], images["new"][2])
