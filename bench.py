@@ -119,6 +119,27 @@ def cpu_oracle_baseline(tris, info, arrays, rays, seconds=12.0):
                       f"oracle/hagrid_oracle.c (CPU restatement of src/traverse.cu), {cores} threads"}
 
 
+def bind_near_gpu(local_rank):
+    """Multi-rank runs: keep this rank's threads (and with them the first touch of its page-locked frame buffers)
+    on the CPUs NVML reports as local to its GPU. Returns a description for the JSON line."""
+    if os.environ.get("HGB_BENCH_NO_AFFINITY"):
+        return "not bound (HGB_BENCH_NO_AFFINITY)"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "not bound (no local CPUs allowed)"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs local to GPU {local_rank}"
+    except Exception as e:                                      # the bench must not depend on NVML
+        return f"not bound ({type(e).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -134,6 +155,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     reference = args.impl == "reference"
 
+    affinity = bind_near_gpu(local_rank) if world > 1 else "not bound (single rank)"
     import torch
     import torch.distributed as dist
     from hagrid_b200 import HIT_PRIM_ID, Library, Scene, scenes
@@ -283,7 +305,7 @@ def main():
                        "timing": "CUDA event pair per step on the legacy default stream, sum over steps, max over ranks"},
             "e2e": {"value": round(e2e_value, 1), "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 16 * n,
                     "ms_per_step": round(e2e_total / e2e_steps, 4), "steps": e2e_steps, "hits_match_device_path": e2e_ok,
-                    "api": "hgb_traverse_grid_host (pinned host buffers)"},
+                    "api": "hgb_traverse_grid_host (pinned host buffers)", "host_affinity_rank0": affinity},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
@@ -293,6 +315,13 @@ def main():
                                  "lives in L2, compulsory HBM traffic is 48 B/ray; see DESIGN.md section 5"},
             "build_ms": {"mean": round(float(build_ms.mean()), 3), "min": round(float(build_ms.min()), 3),
                          "what": "build+merge+flatten+expand, keep-alive, event-timed like src/main.cpp:494-508"},
+            "build_roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                               "algorithmic_bytes": int(48 * tris.shape[0] + 4 * info["num_entries"] + 32 * info["num_cells"] + 4 * info["num_refs"]),
+                               "achieved": round((48 * tris.shape[0] + 4 * info["num_entries"] + 32 * info["num_cells"] + 4 * info["num_refs"])
+                                                 / (float(build_ms.mean()) * 1e6), 2),
+                               "note": "SURVEY 8(d): read the triangles once + write the final grid once, over the whole multi-pass pipeline "
+                                       "(about 60 launches at this size, launch- and latency-bound); per-kernel DRAM throughput of the 2 M-triangle "
+                                       "build is in profiles/r01_build_hair2m_kernels.csv"},
             "hit_fraction": round(float((hits["id"] >= 0).mean()), 4),
         }
         line.update(inc)
