@@ -174,11 +174,17 @@ while time.time() < t_end:
         a.setup_traversal(); b.setup_traversal()
         for name, r in rays:
             for mode in (HIT_STEPS, HIT_PRIM_ID):
-                ha, hb = a.trace(r, mode), b.trace(r, mode)
-                buffers_checked += 1
-                if ha.tobytes() != hb.tobytes():
-                    bad = np.nonzero((ha["id"] != hb["id"]) | (ha["t"].view(np.uint32) != hb["t"].view(np.uint32)))[0]
-                    problems.append(f"hits {name} mode {mode} compressed {compressed}: {len(bad)} of {len(r)} differ, first {int(bad[0]) if len(bad) else -1}")
+                ha = a.trace(r, mode)
+                # 3 = the library's own choice (small buffers: one thread per ray); the others force each kernel in turn
+                for variant in (3, 0, 1, 2, 4):
+                    mine.set_option("traverse_variant", variant)
+                    hb = b.trace(r, mode)
+                    buffers_checked += 1
+                    if ha.tobytes() != hb.tobytes():
+                        bad = np.nonzero((ha["id"] != hb["id"]) | (ha["t"].view(np.uint32) != hb["t"].view(np.uint32)))[0]
+                        problems.append(f"hits {name} mode {mode} compressed {compressed} variant {variant}: {len(bad)} of {len(r)} differ, "
+                                        f"first {int(bad[0]) if len(bad) else -1}")
+                mine.set_option("traverse_variant", 3)
     a.close(); b.close()
     print("DONE " + json.dumps({**what, "stages": stages_checked, "buffers": buffers_checked, "problems": problems,
                                 "flat_box": bool(flat_box)}), flush=True)
