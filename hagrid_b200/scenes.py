@@ -377,6 +377,57 @@ def bounce_rays(tris: np.ndarray, rays: np.ndarray, hit_ids: np.ndarray, hit_t: 
     return out
 
 
+def _mix32(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16); x *= np.uint32(0x7feb352d)
+    x ^= x >> np.uint32(15); x *= np.uint32(0x846ca68b)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def bounce_rays_f32(tris: np.ndarray, rays: np.ndarray, hits: np.ndarray, offset: float, tmax: float, seed: int) -> np.ndarray:
+    """Host restatement of hgb_generate_bounce_rays (include/hagrid_b200.h) in numpy float32, one rounding per
+    operation like the device kernel: what a front end without the device stage would compute on the CPU."""
+    f = np.float32
+    out = rays.copy()
+    ids = hits["id"]
+    idx = np.nonzero((ids >= 0) & (ids < tris.shape[0]))[0]
+    tr = tris[ids[idx]]
+    nx, ny, nz = tr["nx"].astype(f), tr["ny"].astype(f), tr["nz"].astype(f)
+    ln = np.sqrt((nx * nx + ny * ny) + nz * nz)
+    keep = ln > 0
+    idx, nx, ny, nz, ln = idx[keep], nx[keep], ny[keep], nz[keep], ln[keep]
+    nx, ny, nz = nx / ln, ny / ln, nz / ln
+    d, o, t = rays["dir"][idx], rays["org"][idx], hits["t"][idx].astype(f)
+    flip = ((nx * d[:, 0] + ny * d[:, 1]) + nz * d[:, 2]) > 0
+    nx, ny, nz = np.where(flip, -nx, nx), np.where(flip, -ny, ny), np.where(flip, -nz, nz)
+    n3 = np.stack([nx, ny, nz], axis=1)
+    org = (o + d * t[:, None]) + n3 * f(offset)
+    base = _mix32(np.uint32(seed & 0xFFFFFFFF) ^ _mix32(idx.astype(np.uint32)))
+    dx, dy, s = np.zeros(idx.size, f), np.zeros(idx.size, f), np.zeros(idx.size, f)
+    todo = np.ones(idx.size, bool)
+    for k in range(8):
+        x = f(2) * ((_mix32(base + np.uint32(2 * k)) >> np.uint32(8)).astype(f) * f(2.0 ** -24)) - f(1)
+        y = f(2) * ((_mix32(base + np.uint32(2 * k + 1)) >> np.uint32(8)).astype(f) * f(2.0 ** -24)) - f(1)
+        q = x * x + y * y
+        take = todo & (q < 1)
+        dx[take], dy[take], s[take] = x[take], y[take], q[take]
+        todo &= ~take
+    dz = np.sqrt(f(1) - s)
+    zero = np.zeros(idx.size, f)
+    near_x = np.abs(nx) > f(0.9)
+    t1 = np.where(near_x[:, None], np.stack([-nz, zero, nx], axis=1), np.stack([zero, nz, -ny], axis=1)).astype(f)
+    tl = np.sqrt((t1[:, 0] * t1[:, 0] + t1[:, 1] * t1[:, 1]) + t1[:, 2] * t1[:, 2])
+    t1 = t1 / tl[:, None]
+    t2 = np.stack([ny * t1[:, 2] - nz * t1[:, 1], nz * t1[:, 0] - nx * t1[:, 2], nx * t1[:, 1] - ny * t1[:, 0]], axis=1)
+    new_dir = (t1 * dx[:, None] + t2 * dy[:, None]) + n3 * dz[:, None]
+    out["org"][idx] = org
+    out["dir"][idx] = new_dir
+    out["tmin"][idx] = 0.0
+    out["tmax"][idx] = f(tmax)
+    return out
+
+
 # ----------------------------------------------------------------------------- files for the reference CLI
 def write_obj(path, tris: np.ndarray):
     """`v`/`f` only, 9 significant digits so float32 values survive the text round trip."""

@@ -73,6 +73,16 @@ def test_oracle_bounce_equals_the_float32_restatement(name):
         assert got[i].tobytes() == np.asarray(want).tobytes(), i
 
 
+@pytest.mark.parametrize("name", ["soup800", "strands1500", "cornell32"])
+def test_host_numpy_restatement_equals_the_oracle(name):
+    """scenes.bounce_rays_f32 (vectorised numpy float32, used by the benchmark tools as the host procedure)."""
+    g = Golden(name)
+    hits, rays = hits_of(g), g.rays.view(RAY_DTYPE).reshape(-1)
+    for seed in (0, 7, 0x48414752):
+        assert scenes.bounce_rays_f32(g.tris, rays, hits, 2e-3, 9.0, seed).tobytes() == \
+            oracle.bounce_rays(g.tris, rays, hits, 2e-3, 9.0, seed).tobytes()
+
+
 def test_oracle_bounce_properties():
     g = Golden("soup800")
     hits, rays = hits_of(g), g.rays.view(RAY_DTYPE).reshape(-1)

@@ -146,3 +146,37 @@ def test_dynamic_scene_rebuild_and_render_matches_the_reference(lib, ref_lib):
     for k in range(4):
         assert np.array_equal(images["new"][k], images["ref"][k]), k
     assert not np.array_equal(images["new"][0], images["new"][2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["depth", "heat"])
+def test_headless_viewer_writes_the_reference_start_up_frame(lib, tmp_path, mode):
+    """python -m hagrid_b200.view: OBJ in, PPM out; the first frame is the reference's start-up view
+    (eye at the box centre, forward +z, src/main.cpp:572-588) coloured like update_surface."""
+    from hagrid_b200 import view as viewer
+    tris = scenes.atrium(4000, seed=3)
+    obj, ppm = tmp_path / "scene.obj", tmp_path / "frame.ppm"
+    scenes.write_obj(obj, tris)
+    w, h = 128, 96
+    assert viewer.main([str(obj), "-o", str(ppm), "-sx", str(w), "-sy", str(h), "-td", "0.15", "-sd", "3.0", "--mode", mode]) == 0
+    raw = ppm.read_bytes()
+    head = f"P6\n{w} {h}\n255\n".encode()
+    assert raw.startswith(head)
+    got = np.frombuffer(raw[len(head):], np.uint8).reshape(h, w, 3)
+
+    sc = Scene(obj, lib=lib)                       # same loader, so the same triangles and scene box
+    sc.build_all(0.15, 3.0)
+    sc.setup_traversal()
+    gi = sc.info()
+    lo, hi = np.array(gi.bbox_min, np.float32), np.array(gi.bbox_max, np.float32)
+    eye = (lo + hi) * np.float32(0.5)
+    clip = float(np.sqrt(np.sum((hi - lo) * (hi - lo), dtype=np.float32)))
+    cam = oracle.gen_camera(eye, eye + np.array([0, 0, 100], np.float32), (0, 1, 0), 60.0, w / h)
+    hits = sc.trace(oracle.gen_rays(cam, clip, w, h), HIT_STEPS)
+    want = oracle.update_surface({"depth": 0, "heat": 2}[mode], hits, clip, w, h)
+    assert np.array_equal(got, want[..., 2::-1])
+    sc.close()
+    # several frames: numbered files, the camera turns
+    assert viewer.main([str(obj), "-o", str(ppm), "-sx", "64", "-sy", "48", "--frames", "3"]) == 0
+    frames = [(tmp_path / f"frame_{k:04d}.ppm").read_bytes() for k in range(3)]
+    assert len({len(f) for f in frames}) == 1 and frames[0] != frames[1]
