@@ -1,5 +1,6 @@
 """Traversal micro-benchmark on a reference-built grid (run under gpurun, optionally under ncu).
-usage: gpu_traverse_bench.py [primary|long|random] [iters] [variants csv] [ref]"""
+usage: gpu_traverse_bench.py [primary|long|random] [iters] [variants csv] [ref]
+HGB_COMPRESS=0|1 overrides the default (compressed grid for random rays only)."""
 import json
 import sys
 from pathlib import Path
@@ -18,7 +19,8 @@ with_ref = len(sys.argv) > 4 and sys.argv[4] == "ref"
 ref = Library(ROOT / "oracle/_ref/libhagrid_ref.so")
 mine = Library()
 tris = scenes.sponza262k()
-compress = kind == "random"
+import os
+compress = kind == "random" if "HGB_COMPRESS" not in os.environ else os.environ["HGB_COMPRESS"] == "1"
 rays = {"primary": lambda: scenes.default_view(tris), "long": lambda: scenes.default_view(tris, along_long_axis=True),
         "random": lambda: scenes.random_rays(tris, 4194304)}[kind]()
 sr = Scene(tris, lib=ref)
