@@ -185,7 +185,7 @@ def main():
 
     # ---- construction (every rank builds its own replica; reported, not the headline)
     scene = Scene(tris, device=local_rank, keep_alive=True, lib=lib)
-    build_ms = scene.build_all(TOP_DENSITY, SND_DENSITY, ALPHA, EXPANSION, compress=False, warmup=2, iters=5)
+    build_ms = scene.build_all(TOP_DENSITY, SND_DENSITY, ALPHA, EXPANSION, compress=False, warmup=3, iters=10)
     scene.setup_traversal()
     info = scene.info().as_dict()
 
@@ -313,7 +313,8 @@ def main():
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "note": "gather kernel bound by instruction issue and dependent-load latency (ncu: 70 % of peak issue rate, 22 of 32 lanes active): the scene "
                                  "lives in L2, compulsory HBM traffic is 48 B/ray; see DESIGN.md section 5"},
-            "build_ms": {"mean": round(float(build_ms.mean()), 3), "min": round(float(build_ms.min()), 3),
+            "build_ms": {"mean": round(float(build_ms.mean()), 3), "median": round(float(np.median(build_ms)), 3),
+                         "min": round(float(build_ms.min()), 3), "iters": int(build_ms.shape[0]),
                          "what": "build+merge+flatten+expand, keep-alive, event-timed like src/main.cpp:494-508"},
             "build_roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
                                "algorithmic_bytes": int(48 * tris.shape[0] + 4 * info["num_entries"] + 32 * info["num_cells"] + 4 * info["num_refs"]),
