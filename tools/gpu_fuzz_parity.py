@@ -1,7 +1,7 @@
 """Differential fuzzing on one GPU (run under gpurun): random scenes, random construction parameters and random
 ray buffers through the reference (rebuilt for sm_100a) and through this library; every stage's grid must be
 byte-identical and every hit buffer bit-identical (step counts and primitive ids, Cell and SmallCell grids).
-usage: gpu_fuzz_parity.py [seconds] [first_seed]     prints one JSON summary line; failures are listed in full."""
+usage: gpu_fuzz_parity.py [--large] [seconds] [first_seed]     prints one JSON summary line; failures are listed in full."""
 import json, sys, time
 from pathlib import Path
 import numpy as np
@@ -9,6 +9,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from hagrid_b200 import HIT_PRIM_ID, HIT_STEPS, Library, Scene, scenes
 
+large = "--large" in sys.argv          # scenes of 50-200 K triangles, ray buffers big enough for the resident-warp kernels
+sys.argv = [a for a in sys.argv if a != "--large"]
 worker = len(sys.argv) > 1 and sys.argv[1] == "--worker"
 args = sys.argv[2:] if worker else sys.argv[1:]
 budget = float(args[0]) if len(args) > 0 else 120.0
@@ -23,7 +25,7 @@ if not worker:
     t_end = time.time() + budget
     seed = seed0
     while time.time() < t_end - 3:
-        res = subprocess.run([sys.executable, __file__, "--worker", str(t_end - time.time()), str(seed)],
+        res = subprocess.run([sys.executable, __file__, "--worker", str(t_end - time.time()), str(seed)] + (["--large"] if large else []),
                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         started = None
         for line in res.stdout.splitlines():
@@ -77,7 +79,7 @@ def soup(rng, n):
 
 def make_scene(rng):
     kind = rng.integers(0, 5)
-    n = int(rng.choice([1, 2, 7, 33, 150, 800, 3000, 12000]))
+    n = int(rng.choice([50000, 120000, 200000])) if large else int(rng.choice([1, 2, 7, 33, 150, 800, 3000, 12000]))
     if kind == 0:
         return "soup", soup(rng, n)
     if kind == 1:
@@ -97,7 +99,7 @@ def make_rays(rng, tris):
     lo, hi = scenes.scene_bbox(tris)
     diag = float(np.linalg.norm(hi - lo)) or 1.0
     out = []
-    n = int(rng.choice([1, 31, 257, 4096, 20000]))
+    n = int(rng.choice([140000, 300000])) if large else int(rng.choice([1, 31, 257, 4096, 20000]))
     r = scenes.random_rays(tris, n, seed=int(rng.integers(1 << 30)))
     if rng.uniform() < 0.5:                                 # origins outside the box, finite range
         r["org"] = (lo + (hi - lo) * rng.uniform(-1.0, 2.0, size=(n, 3))).astype(np.float32)
@@ -109,6 +111,8 @@ def make_rays(rng, tris):
         r["dir"][1::7, (k + 1) % 3] = 0.0
     out.append(("random", r))
     w, h = [(64, 64), (128, 36), (200, 52), (96, 40)][int(rng.integers(0, 4))]
+    if large:
+        w, h = [(1280, 720), (1024, 512), (960, 540)][int(rng.integers(0, 3))]
     center = 0.5 * (lo + hi)
     eye = center + (hi - lo) * rng.uniform(-0.9, 0.9, size=3).astype(np.float32)
     target = center + (hi - lo) * rng.uniform(-0.2, 0.2, size=3).astype(np.float32)
