@@ -29,6 +29,18 @@ def shard_bounds(num_rays: int, rank: int, world: int, granule: int = 128) -> tu
     return min(first * granule, num_rays), min(last * granule, num_rays)
 
 
+def interleaved_bands(num_rays: int, rank: int, world: int, granule: int) -> np.ndarray:
+    """Indices of rank's rays when bands of `granule` rays are dealt round-robin (band k goes to rank k % world):
+    for camera rasters with granule = raster_granule(width) every rank gets 4-row bands from all over the image, which
+    evens out cheap and expensive regions (contiguous blocks leave the rank with the expensive part of the image as the
+    slowest). The rank's rays, stored in this order, are again a raster of the same width."""
+    if world <= 0 or not (0 <= rank < world) or granule <= 0:
+        raise ValueError("bad rank/world/granule")
+    units = (num_rays + granule - 1) // granule
+    parts = [np.arange(u * granule, min((u + 1) * granule, num_rays), dtype=np.int64) for u in range(rank, units, world)]
+    return np.concatenate(parts) if parts else np.empty(0, dtype=np.int64)
+
+
 def raster_granule(width: int, tile_h: int = 4) -> int:
     """Granule that keeps rank boundaries on tile-row boundaries of a `width`-pixel raster."""
     return width * tile_h

@@ -1,6 +1,7 @@
 """CPU tier: host-side multi-GPU logic (ray sharding + counter reduction), world_size 2 over gloo."""
 import os
 import socket
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -26,6 +27,17 @@ def test_raster_granule_keeps_tile_rows_whole():
     for r in range(8):
         a, b = sharding.shard_bounds(1920 * 1080, r, 8, g)
         assert a % (1920 * 4) == 0 and (b % (1920 * 4) == 0 or b == 1920 * 1080)
+
+
+@pytest.mark.parametrize("n,world,granule", [(2073600, 8, 1920 * 4), (2073600, 3, 1920 * 4), (1000, 4, 128), (0, 2, 64), (130, 2, 64)])
+def test_interleaved_bands_partition_exactly(n, world, granule):
+    parts = [sharding.interleaved_bands(n, r, world, granule) for r in range(world)]
+    merged = np.sort(np.concatenate(parts))
+    assert np.array_equal(merged, np.arange(n))
+    for r, p in enumerate(parts):
+        assert np.all(np.diff(p) > 0)
+        assert np.all((p // granule) % world == r)                      # whole bands, dealt round-robin
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= granule
 
 
 def test_bad_rank_rejected():
@@ -78,3 +90,25 @@ def test_two_rank_sharded_trace_equals_single_process(tmp_path):
 def test_reduce_counters_without_process_group_is_identity():
     local = np.array([3.0, 10.0, 0.5])
     assert np.array_equal(sharding.reduce_counters(local, None), local)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["blocks", "bands"])
+def test_frame_sharded_over_the_gpus_of_the_node_equals_the_unsharded_frame(mode):
+    """NCCL tier (needs at least two GPUs): tools/gpu_sharded_frame.py under torchrun."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("one GPU")
+    root = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+                          str(root / "tools" / "gpu_sharded_frame.py"), "5", mode], capture_output=True, text=True, timeout=400)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["n_gpus"] == world and sum(line["shard_sizes"]) == line["rays"] and line["sharding"] == mode
+    assert line["hits_identical_to_unsharded"] and line["host_path_identical"]
+    assert line["hits_counted_by_all_reduce"] == line["hits_in_unsharded_trace"]
