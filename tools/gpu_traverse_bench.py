@@ -1,6 +1,6 @@
 """Traversal micro-benchmark on a reference-built grid (run under gpurun, optionally under ncu).
 usage: gpu_traverse_bench.py [primary|long|random] [iters] [variants csv] [ref]
-HGB_COMPRESS=0|1 overrides the default (compressed grid for random rays only)."""
+HGB_COMPRESS=0|1 overrides the default (compressed grid for random rays only); HGB_FRAME=WxH sets the size of the primary view."""
 import json
 import sys
 from pathlib import Path
@@ -21,7 +21,8 @@ mine = Library()
 tris = scenes.sponza262k()
 import os
 compress = kind == "random" if "HGB_COMPRESS" not in os.environ else os.environ["HGB_COMPRESS"] == "1"
-rays = {"primary": lambda: scenes.default_view(tris), "long": lambda: scenes.default_view(tris, along_long_axis=True),
+W_, H_ = (int(v) for v in os.environ.get("HGB_FRAME", "1920x1080").split("x"))
+rays = {"primary": lambda: scenes.default_view(tris, W_, H_), "long": lambda: scenes.default_view(tris, along_long_axis=True),
         "random": lambda: scenes.random_rays(tris, 4194304)}[kind]()
 sr = Scene(tris, lib=ref)
 sr.build_grid(0.15, 3.0); sr.merge_grid(0.995); sr.flatten_grid(); sr.expand_grid(3)
