@@ -14,10 +14,10 @@
 //     step and those that own references to test (kernel B, `__ballot_sync` population counts);
 //   * host-buffer frames are cut into chunks whose upload, traversal and download overlap.
 //
-// ncu (profiles/): both kernels issue at 72-78 % of the SM's peak rate; the coherent kernel is bound by
-// instruction issue (2 090 warp instructions per 32 rays at 23 of 32 lanes active), the incoherent
-// one by the latency of its dependent L2 loads. The grid, the references and the triangles (tens of
-// MB) live in the 126 MB L2; compulsory HBM traffic is 32 B/ray in + 16 B/hit out.
+// ncu (profiles/): the coherent kernel issues at 70 % of the SM's peak rate (1 756 warp instructions per 32
+// rays at 22 of 32 lanes active) and is bound by instruction issue and dependent-load latency, the incoherent
+// one (59 %) by the latency of its dependent L2 loads under scattered access. The grid, the references and
+// the triangles a view touches live in the 126 MB L2; compulsory HBM traffic is 32 B/ray in + 16 B/hit out.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
