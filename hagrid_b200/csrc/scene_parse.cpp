@@ -15,6 +15,7 @@
 // like the reference's failed getline does (src/load_obj.cpp:103-105), but is reported as an error.
 #include <algorithm>
 #include <cctype>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,18 +48,85 @@ struct Chunk {
 
 inline const char* skip_spaces(const char* p) { while (std::isspace((unsigned char)*p)) p++; return p; }
 
+/// strtof for the numbers OBJ files hold, same value and same end pointer: plain decimals of at most 19 digits
+/// with a small exponent are converted through one exact double operation (integer mantissa times or divided by
+/// an exactly representable power of ten: the double is correctly rounded) and rounded to float. Rounding twice
+/// can only differ from rounding once when that double sits exactly half-way between two floats; then, and for
+/// everything else (inf, nan, hex floats, long mantissas, huge exponents, results outside the normal float range,
+/// no digits at all), the C library decides.
+float parse_float(const char* text, char** end) {
+    static const double kPow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                      1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    const char* p = skip_spaces(text);
+    bool negative = false;
+    if (*p == '-' || *p == '+') { negative = *p == '-'; p++; }
+    uint64_t mantissa = 0;
+    int digits = 0, exp10 = 0;
+    bool any = false;
+    while (*p >= '0' && *p <= '9') {
+        any = true;
+        if (mantissa || *p != '0') { if (++digits > 19) return std::strtof(text, end); mantissa = mantissa * 10 + uint64_t(*p - '0'); }
+        p++;
+    }
+    if (*p == '.') {
+        p++;
+        while (*p >= '0' && *p <= '9') {
+            any = true;
+            if (mantissa || *p != '0') { if (++digits > 19) return std::strtof(text, end); mantissa = mantissa * 10 + uint64_t(*p - '0'); }
+            exp10--;
+            p++;
+        }
+    }
+    if (!any) return std::strtof(text, end);
+    if (*p == 'e' || *p == 'E') {
+        const char* q = p + 1;
+        bool exp_negative = false;
+        if (*q == '-' || *q == '+') { exp_negative = *q == '-'; q++; }
+        if (*q >= '0' && *q <= '9') {
+            int e = 0;
+            while (*q >= '0' && *q <= '9') { if (e < 10000) e = e * 10 + (*q - '0'); q++; }
+            exp10 += exp_negative ? -e : e;
+            p = q;
+        }
+    } else if (*p == 'x' || *p == 'X') {
+        return std::strtof(text, end);                       // "0x..." is a hexadecimal float for strtof
+    }
+    if (mantissa == 0) { *end = const_cast<char*>(p); return negative ? -0.0f : 0.0f; }
+    if (mantissa >= (1ull << 53) || exp10 < -22 || exp10 > 22) return std::strtof(text, end);
+    const double d = exp10 < 0 ? double(mantissa) / kPow10[-exp10] : double(mantissa) * kPow10[exp10];
+    uint64_t bits;
+    std::memcpy(&bits, &d, sizeof(bits));
+    if ((bits & 0x1FFFFFFFull) == 0x10000000ull || d < 1.2e-38 || d > 3.4e38) return std::strtof(text, end);
+    *end = const_cast<char*>(p);
+    const float f = float(d);
+    return negative ? -f : f;
+}
+
+/// strtol(base 10) for the indices of a face; long digit strings go to the C library
+long parse_index(const char* text, char** end) {
+    const char* p = skip_spaces(text);
+    bool negative = false;
+    if (*p == '-' || *p == '+') { negative = *p == '-'; p++; }
+    if (!(*p >= '0' && *p <= '9')) return std::strtol(text, end, 10);
+    long value = 0;
+    int digits = 0;
+    while (*p >= '0' && *p <= '9') { if (++digits > 17) return std::strtol(text, end, 10); value = value * 10 + (*p - '0'); p++; }
+    *end = const_cast<char*>(p);
+    return negative ? -value : value;
+}
+
 /// read_index, src/load_obj.cpp:42-76
 bool read_corner(const char*& p, int& v, int& t, int& n) {
     const char* base = skip_spaces(p);
     if (!std::isdigit((unsigned char)*base) && *base != '-') return false;
     v = t = n = 0;
     char* next;
-    v = int(std::strtol(base, &next, 10)); base = skip_spaces(next);
+    v = int(parse_index(base, &next)); base = skip_spaces(next);
     if (*base == '/') {
         base++;
-        if (*base != '/') { t = int(std::strtol(base, &next, 10)); base = next; }
+        if (*base != '/') { t = int(parse_index(base, &next)); base = next; }
         base = skip_spaces(base);
-        if (*base == '/') { base++; n = int(std::strtol(base, &next, 10)); base = next; }
+        if (*base == '/') { base++; n = int(parse_index(base, &next)); base = next; }
     }
     p = base;
     return true;
@@ -87,7 +155,7 @@ void parse_chunk(Chunk& c) {
             if (ptr[1] == ' ' || ptr[1] == '\t') {
                 char* next;
                 vec3 v;
-                v.x = std::strtof(ptr + 1, &next); v.y = std::strtof(next, &next); v.z = std::strtof(next, &next);
+                v.x = parse_float(ptr + 1, &next); v.y = parse_float(next, &next); v.z = parse_float(next, &next);
                 c.vertices.push_back(v);
             } else if (ptr[1] == 'n') c.num_normals++;
             else if (ptr[1] == 't') c.num_texcoords++;

@@ -56,6 +56,49 @@ def test_parallel_host_parser_matches_the_reference_loader(tmp_path, name, threa
     assert tris_from(verts, idx).tobytes() == Z[f"{name}_tris"].tobytes()
 
 
+def test_number_parsing_equals_strtof_on_adversarial_input(tmp_path):
+    """The host parser converts plain decimals itself (one exact double operation, then float) and leaves the rest to
+    strtof; the oracle calls the C library's strtof for every number like the reference (src/load_obj.cpp:119-122).
+    Same bits and same end-of-number positions on: random decimals of every length, floats' exact half-way points
+    (where rounding twice would differ from rounding once), range limits, and everything strtof accepts besides."""
+    import struct
+    rng = np.random.default_rng(12)
+    tokens = ["inf", "-inf", "nan", "0x1p3", "-0x1.8p1", "1e", "1e+", "2.5e-", ".", "-.5", "+.5e1", "5.", "1e400", "-1e400",
+              "1e-400", "1e-40", "1.1754944e-38", "1.1754942e-38", "3.4028235e38", "3.4028236e38", "3.5e38", "0", "-0", "-0.0e5",
+              "00012.5000", "1E5", "1d5", "1_000", "1e0005", "1e99999999999", "12345678901234567890", "1234567890123456789",
+              "0.00000000000000000001234", "123456789012345678901234567890e-25", "9007199254740993", "9007199254740992e-3",
+              "8388608.5", "8388609.5", "16777217", "16777219", "33554434", "0.1", "0.3", "1e23", "1e22", "1e-22", "1e-23"]
+    for _ in range(1500):                                     # random decimals: 1-21 digits, point anywhere, optional exponent
+        digits = "".join(rng.choice(list("0123456789"), size=int(rng.integers(1, 22))))
+        cut = int(rng.integers(0, len(digits) + 1))
+        text = digits[:cut] + "." + digits[cut:] if rng.random() < 0.8 else digits
+        if rng.random() < 0.4:
+            text += rng.choice(["e", "E"]) + rng.choice(["", "+", "-"]) + str(int(rng.integers(0, 45)))
+        tokens.append(("-" if rng.random() < 0.3 else "") + text)
+    for _ in range(1500):                                     # exact half-way points between neighbouring floats, and their neighbours
+        f = np.float32(rng.uniform(-1, 1) * 10.0 ** rng.integers(-6, 9))
+        g = np.nextafter(f, np.float32(np.inf))
+        mid = (float(f) + float(g)) / 2                       # exact in double
+        tokens += [repr(mid), "%.17g" % mid, "%.9g" % mid, "%.8g" % float(f), "%.9g" % float(g)]
+        from decimal import Decimal
+        tokens.append(format(Decimal(mid), "f"))              # the half-way point written out in full
+    while len(tokens) % 3:
+        tokens.append("1")
+    path = tmp_path / "numbers.obj"
+    with open(path, "w") as f:
+        for i in range(0, len(tokens), 3):
+            f.write("v %s %s %s\n" % tuple(tokens[i:i + 3]))
+        f.write("f 1 2 3\n")
+    lines = len(tokens) // 3
+    ref = np.array([obj_oracle._strtof3((" %s %s %s" % tuple(tokens[3 * i:3 * i + 3])).encode()) for i in range(lines)],
+                   dtype=np.float32).view(np.uint32)
+    for threads in (1, 5):
+        verts, idx = parse_obj(path, threads)
+        got = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)[-lines:].view(np.uint32)
+        bad = np.nonzero((got != ref).any(axis=1))[0]
+        assert len(bad) == 0, (tokens[3 * bad[0]: 3 * bad[0] + 3], got[bad[0]], ref[bad[0]])
+
+
 def test_chunk_boundaries_do_not_change_the_result(tmp_path):
     """A file large enough to be cut into many chunks, relative indices reaching across chunk boundaries."""
     rng = np.random.default_rng(11)
