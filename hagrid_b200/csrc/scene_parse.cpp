@@ -19,7 +19,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "scene_ingest.h"
 
@@ -199,23 +204,36 @@ void run_parallel(int count, F&& body) {
 
 bool parse_obj(const std::string& path, int threads, ObjGeometry& out) {
     out.vertices.clear(); out.indices.clear(); out.error.clear();
-    std::FILE* fp = std::fopen(path.c_str(), "rb");
-    if (!fp) { out.error = "cannot open " + path; return false; }
-    std::fseek(fp, 0, SEEK_END);
-    const long size = std::ftell(fp);
-    std::fseek(fp, 0, SEEK_SET);
-    std::vector<char> text(size_t(size) + 1);
-    const size_t got = size > 0 ? std::fread(text.data(), 1, size_t(size), fp) : 0;
-    std::fclose(fp);
-    if (got != size_t(size)) { out.error = "cannot read " + path; return false; }
-    text[size_t(size)] = '\0';
-
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) { out.error = "cannot open " + path; return false; }
+    struct stat info;
+    if (::fstat(fd, &info) != 0 || info.st_size < 0) { ::close(fd); out.error = "cannot read " + path; return false; }
+    const long size = long(info.st_size);
     if (threads <= 0) threads = int(std::thread::hardware_concurrency());
     threads = std::max(1, std::min(threads, int(size / (1 << 16)) + 1));
+    // the file goes into an uninitialised buffer, every thread reading its own slice: the copy out of the page cache
+    // and the page faults of the fresh buffer are the larger part of a cold sequential read
+    std::unique_ptr<char[]> text(new char[size_t(size) + 1]);
+    std::vector<char> slice_ok(size_t(threads), 0);
+    run_parallel(threads, [&](int i) {
+        size_t at = size_t(size) * size_t(i) / size_t(threads);
+        const size_t stop = size_t(size) * size_t(i + 1) / size_t(threads);
+        while (at < stop) {
+            const ssize_t n = ::pread(fd, text.get() + at, stop - at, off_t(at));
+            if (n <= 0) return;
+            at += size_t(n);
+        }
+        slice_ok[size_t(i)] = 1;
+    });
+    ::close(fd);
+    for (char ok : slice_ok)
+        if (!ok) { out.error = "cannot read " + path; return false; }
+    text[size_t(size)] = '\0';
+
     std::vector<Chunk> chunks;
     chunks.resize(static_cast<size_t>(threads));
     {
-        const char* base = text.data();
+        const char* base = text.get();
         const char* end = base + size;
         const char* cur = base;
         for (int i = 0; i < threads; i++) {
