@@ -51,7 +51,10 @@ struct Chunk {
     std::string error;
 };
 
-inline const char* skip_spaces(const char* p) { while (std::isspace((unsigned char)*p)) p++; return p; }
+// isspace / isdigit of the "C" locale (the only one the loader ever runs in), without the library call
+inline bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
+inline const char* skip_spaces(const char* p) { while (is_space(*p)) p++; return p; }
 
 /// strtof for the numbers OBJ files hold, same value and same end pointer: plain decimals of at most 19 digits
 /// with a small exponent are converted through one exact double operation (integer mantissa times or divided by
@@ -123,7 +126,7 @@ long parse_index(const char* text, char** end) {
 /// read_index, src/load_obj.cpp:42-76
 bool read_corner(const char*& p, int& v, int& t, int& n) {
     const char* base = skip_spaces(p);
-    if (!std::isdigit((unsigned char)*base) && *base != '-') return false;
+    if (!is_digit(*base) && *base != '-') return false;
     v = t = n = 0;
     char* next;
     v = int(parse_index(base, &next)); base = skip_spaces(next);
@@ -138,23 +141,21 @@ bool read_corner(const char*& p, int& v, int& t, int& n) {
 }
 
 void parse_chunk(Chunk& c) {
-    char line[kMaxLine];
-    const char* p = c.begin;
-    while (p < c.end) {
-        const char* eol = static_cast<const char*>(std::memchr(p, '\n', size_t(c.end - p)));
-        const char* stop = eol ? eol : c.end;
-        const size_t len = size_t(stop - p);
-        if (len >= kMaxLine - 1) { c.error = "line longer than 1022 characters"; return; }
-        std::memcpy(line, p, len);
-        line[len] = '\0';
-        p = eol ? eol + 1 : c.end;
-
-        const char* ptr = skip_spaces(line);
+    // Lines are terminated in place (the buffer is private to the parse and chunks do not overlap): the numbers of a
+    // line must not run on into the next one, which is what the reference's getline into a line buffer guarantees.
+    char* p = const_cast<char*>(c.begin);
+    char* const chunk_end = const_cast<char*>(c.end);
+    while (p < chunk_end) {
+        char* eol = static_cast<char*>(std::memchr(p, '\n', size_t(chunk_end - p)));
+        char* stop = eol ? eol : chunk_end;
+        if (size_t(stop - p) >= kMaxLine - 1) { c.error = "line longer than 1022 characters"; return; }
+        *stop = '\0';                    // the '\n', or the terminator behind the last line of the file
+        const char* ptr = skip_spaces(p);
+        p = eol ? eol + 1 : chunk_end;
         if (*ptr == '\0' || *ptr == '#') continue;
         {   // remove_eol, src/load_obj.cpp:22-30
-            char* q = const_cast<char*>(ptr);
-            int i = int(std::strlen(q)) - 1;
-            while (i > 0 && std::isspace((unsigned char)q[i])) q[i--] = '\0';
+            char* q = stop - 1;
+            while (q > ptr && is_space(*q)) *q-- = '\0';
         }
         if (*ptr == 'v') {
             if (ptr[1] == ' ' || ptr[1] == '\t') {
@@ -165,7 +166,7 @@ void parse_chunk(Chunk& c) {
             } else if (ptr[1] == 'n') c.num_normals++;
             else if (ptr[1] == 't') c.num_texcoords++;
             else { c.error = "invalid vertex"; return; }
-        } else if (*ptr == 'f' && std::isspace((unsigned char)ptr[1])) {
+        } else if (*ptr == 'f' && is_space(ptr[1])) {
             RawFace f;
             f.count = 0;
             const char* q = ptr + 2;
@@ -173,8 +174,8 @@ void parse_chunk(Chunk& c) {
             if (f.count < 3) { c.error = "invalid face"; return; }
             f.verts_before = int(c.vertices.size()); f.texs_before = c.num_texcoords; f.norms_before = c.num_normals;
             c.faces.push_back(f);
-        } else if ((*ptr == 'g' || *ptr == 'o' || *ptr == 's') && std::isspace((unsigned char)ptr[1])) {
-        } else if ((!std::strncmp(ptr, "usemtl", 6) || !std::strncmp(ptr, "mtllib", 6)) && std::isspace((unsigned char)ptr[6])) {
+        } else if ((*ptr == 'g' || *ptr == 'o' || *ptr == 's') && is_space(ptr[1])) {
+        } else if ((!std::strncmp(ptr, "usemtl", 6) || !std::strncmp(ptr, "mtllib", 6)) && is_space(ptr[6])) {
         } else { c.error = std::string("unknown command ") + ptr; return; }
     }
 }
