@@ -47,6 +47,8 @@ void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays,
                         Ray* dev_rays, Hit* dev_hits, bool prim_ids);
 bool set_traversal_option(const char* key, int value);
 unsigned long long kernel_launch_count();
+void trim_device_pool();
+void note_triangle_array(const Tri* tris, int num_tris);
 #endif
 }
 
@@ -63,11 +65,12 @@ struct hgb_scene {
     int frame_capacity;
     unsigned* frame_pixels;
     int pixel_capacity;
-    unsigned long long grid_epoch;      // bumped by everything that changes the grid
+    unsigned long long grid_epoch;      // bumped by everything that changes the grid or the triangles
+    unsigned long long setup_epoch;     // grid_epoch at the last hgb_setup_traversal (~0: never)
 
     hgb_scene(int dev, bool keep)
         : mem(keep), tris(nullptr), num_tris(0), device(dev),
-          frame_rays(nullptr), frame_hits(nullptr), frame_capacity(0), frame_pixels(nullptr), pixel_capacity(0), grid_epoch(0)
+          frame_rays(nullptr), frame_hits(nullptr), frame_capacity(0), frame_pixels(nullptr), pixel_capacity(0), grid_epoch(0), setup_epoch(~0ull)
     {
         grid.entries = nullptr;
         grid.ref_ids = nullptr;
@@ -111,11 +114,16 @@ static void release_grid(hgb_scene* s) {
     s->grid.small_cells = nullptr;
 }
 
-// The traversal constants are per process (src/traverse.cu:7-12): remember which grid they describe so
-// that tracing another scene without a new hgb_setup_traversal is an error code, not a wild walk.
-static struct { const hgb_scene* scene; unsigned long long epoch; } g_setup = {nullptr, 0};
-
-static bool setup_matches(const hgb_scene* s) { return g_setup.scene == s && g_setup.epoch == s->grid_epoch; }
+// hgb_setup_traversal must follow every change of a scene's grid or triangles (the reference's call order,
+// src/main.cpp:536-549): tracing a scene whose setup is stale is an error code. The state is per scene --
+// any number of scenes, on any devices, can be set up and traced side by side.
+#ifdef HGB_REFERENCE_BUILD
+// ... except in the reference build, whose traversal constants are per process (src/traverse.cu:7-12)
+static const hgb_scene* g_ref_setup_scene = nullptr;
+static bool setup_matches(const hgb_scene* s) { return g_ref_setup_scene == s && s->setup_epoch == s->grid_epoch; }
+#else
+static bool setup_matches(const hgb_scene* s) { return s->setup_epoch == s->grid_epoch; }
+#endif
 
 /// Device staging buffers of a host-buffer frame, from the scene's pool
 static void reserve_frame(hgb_scene* s, int num_rays) {
@@ -178,8 +186,11 @@ hgb_scene* hgb_scene_create(int device, int keep_alive) {
 
 void hgb_scene_destroy(hgb_scene* s) {
     if (!s) return;
-    if (g_setup.scene == s) g_setup.scene = nullptr;
-    if (bind(s)) {
+#ifdef HGB_REFERENCE_BUILD
+    if (g_ref_setup_scene == s) g_ref_setup_scene = nullptr;
+#endif
+    const bool bound = bind(s);
+    if (bound) {
         cudaDeviceSynchronize();
         release_grid(s);
         s->mem.free(s->tris);
@@ -187,12 +198,16 @@ void hgb_scene_destroy(hgb_scene* s) {
         s->mem.free(s->frame_hits);
         s->mem.free(s->frame_pixels);
     }
-    delete s;
+    delete s;               // ~MemManager hands every slot back, also what keep-alive mode retained
+#ifndef HGB_REFERENCE_BUILD
+    if (bound) trim_device_pool();
+#endif
 }
 
 int hgb_scene_set_tris(hgb_scene* s, const void* host_tris, int num_tris) {
     if (!bind(s)) return -1;
     if (!host_tris || num_tris <= 0) return fail("set_tris: empty triangle array");
+    s->grid_epoch++;            // the grid indexes the old triangle array: stale until rebuilt and set up again
     s->mem.free(s->tris);
     s->tris = s->mem.alloc<Tri>(num_tris);
     s->mem.copy<Copy::HST_TO_DEV>(s->tris, static_cast<const Tri*>(host_tris), num_tris);
@@ -203,6 +218,7 @@ int hgb_scene_set_tris(hgb_scene* s, const void* host_tris, int num_tris) {
 int hgb_scene_load_obj(hgb_scene* s, const char* path, int threads) {
     if (!bind(s)) return -1;
     if (!path) return fail("load_obj: null path");
+    s->grid_epoch++;
 #ifdef HGB_REFERENCE_BUILD
     (void)threads;
     int n = 0;
@@ -324,8 +340,10 @@ int hgb_setup_traversal(hgb_scene* s) {
 #ifdef HGB_REFERENCE_BUILD
     setup_traversal_pid(s->grid);
 #endif
-    g_setup.scene = s;
-    g_setup.epoch = s->grid_epoch;
+#ifdef HGB_REFERENCE_BUILD
+    g_ref_setup_scene = s;
+#endif
+    s->setup_epoch = s->grid_epoch;
     return 0;
 }
 
@@ -567,6 +585,20 @@ int hgb_grid_upload(hgb_scene* s, const hgb_grid_info* info,
     if (!bind(s)) return -1;
     if (!info || !host_entries || !host_cells) return fail("grid_upload: null argument");
     if (info->num_offsets < 0 || info->num_offsets > HGB_MAX_LEVELS) return fail("grid_upload: bad offsets");
+    // validate before the scene is touched: a bad header must leave the old grid in place
+    if (info->num_cells <= 0 || info->num_entries <= 0 || info->num_refs < 0) return fail("grid_upload: bad counts");
+    if (info->num_refs > 0 && !host_refs) return fail("grid_upload: null reference array");
+    if (info->shift < 0 || info->shift > 20) return fail("grid_upload: bad shift");
+    long long top = 1;
+    for (int k = 0; k < 3; k++) {
+        if (info->dims[k] <= 0 || ((long long)info->dims[k] << info->shift) > (1ll << 30)) return fail("grid_upload: bad dims");
+        if (!(info->bbox_max[k] > info->bbox_min[k])) return fail("grid_upload: empty bounding box");
+        top *= info->dims[k];
+    }
+    if (top > info->num_entries) return fail("grid_upload: fewer entries than top-level cells");
+    for (int i = 0; i < info->num_offsets; i++)
+        if (info->offsets[i] < 0 || info->offsets[i] > info->num_entries || (i > 0 && info->offsets[i] < info->offsets[i - 1]))
+            return fail("grid_upload: bad offsets");
     release_grid(s);
     Grid& g = s->grid;
     g.bbox = BBox(vec3(info->bbox_min[0], info->bbox_min[1], info->bbox_min[2]),
@@ -577,15 +609,15 @@ int hgb_grid_upload(hgb_scene* s, const hgb_grid_info* info,
     g.num_entries = info->num_entries;
     g.num_refs = info->num_refs;
     g.offsets.assign(info->offsets, info->offsets + info->num_offsets);
+#ifndef HGB_REFERENCE_BUILD
+    if (s->tris) note_triangle_array(s->tris, s->num_tris);
+#endif
 
     g.entries = s->mem.alloc<Entry>(g.num_entries);
     s->mem.copy<Copy::HST_TO_DEV>(g.entries, static_cast<const Entry*>(host_entries), g.num_entries);
     // One spare element so an empty reference array still owns a slot.
     g.ref_ids = s->mem.alloc<int>(size_t(g.num_refs) + 1);
-    if (g.num_refs) {
-        if (!host_refs) return fail("grid_upload: null reference array");
-        s->mem.copy<Copy::HST_TO_DEV>(g.ref_ids, static_cast<const int*>(host_refs), g.num_refs);
-    }
+    if (g.num_refs) s->mem.copy<Copy::HST_TO_DEV>(g.ref_ids, static_cast<const int*>(host_refs), g.num_refs);
     if (info->compressed) {
         g.small_cells = s->mem.alloc<SmallCell>(g.num_cells);
         s->mem.copy<Copy::HST_TO_DEV>(g.small_cells, static_cast<const SmallCell*>(host_cells), g.num_cells);

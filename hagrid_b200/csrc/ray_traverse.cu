@@ -19,15 +19,33 @@
 // one (59 %) by the latency of its dependent L2 loads under scattered access. The grid, the references and
 // the triangles a view touches live in the 126 MB L2; compulsory HBM traffic is 32 B/ray in + 16 B/hit out.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "device_math.cuh"
 #include "runtime.h"
 #include "traverse.h"
+
+// Build-time tuning knobs of the tile kernel (tools/gpu_tile_variants.py builds the alternatives)
+#ifndef HGB_TILE_BLOCKS
+#define HGB_TILE_BLOCKS 10
+#endif
+#ifndef HGB_REF_UNROLL
+#define HGB_REF_UNROLL 0                 // 0: ptxas decides (it unrolls four-fold)
+#endif
+#define HGB_STR2(x) #x
+#define HGB_STR(x) HGB_STR2(x)
+#if HGB_REF_UNROLL > 0
+#define HGB_REF_LOOP_PRAGMA _Pragma(HGB_STR(unroll HGB_REF_UNROLL))
+#else
+#define HGB_REF_LOOP_PRAGMA
+#endif
 
 namespace hagrid {
 
@@ -45,8 +63,26 @@ struct TraversalParams {
     float inv_x, inv_y, inv_z;          // virtual dims / extents
 };
 
-TraversalParams g_params;
-bool g_params_set = false;
+/// The constants are a pure function of the host-side Grid (src/traverse.cu:97-101 computes them once per
+/// setup_traversal and keeps them in __constant__ memory, one set per process). Here every launch derives them
+/// from the grid it is given and passes them as a __grid_constant__ kernel parameter: no process-wide state,
+/// any number of scenes, devices and host threads side by side.
+TraversalParams params_of(const Grid& grid) {
+    // Host IEEE arithmetic, same expressions as src/traverse.cu:97-101.
+    const vec3 extents = grid.bbox.extents();
+    const ivec3 dims = grid.dims << grid.shift;
+    const vec3 inv = vec3(dims) / extents;
+    const vec3 cell = extents / vec3(dims);
+    TraversalParams P;
+    P.dims_x = dims.x; P.dims_y = dims.y; P.dims_z = dims.z;
+    P.top_x = dims.x >> grid.shift; P.top_y = dims.y >> grid.shift;
+    P.shift = grid.shift;
+    P.min_x = grid.bbox.min.x; P.min_y = grid.bbox.min.y; P.min_z = grid.bbox.min.z;
+    P.max_x = grid.bbox.max.x; P.max_y = grid.bbox.max.y; P.max_z = grid.bbox.max.z;
+    P.cell_x = cell.x; P.cell_y = cell.y; P.cell_z = cell.z;
+    P.inv_x = inv.x; P.inv_y = inv.y; P.inv_z = inv.z;
+    return P;
+}
 
 struct RayState {
     float ox, oy, oz, tmin;
@@ -284,6 +320,7 @@ __device__ __forceinline__ void walk(RayState& r, const TraversalParams& P, cons
                 for (int ref = __ldg(ref_ids + cur++); ref >= 0; ref = __ldg(ref_ids + cur++)) intersect_tri(r, tris, ref);
             r.steps += 1 + (cur - cell.begin);
         } else {
+            HGB_REF_LOOP_PRAGMA
             for (int cur = cell.begin; cur < cell.end; cur++) intersect_tri(r, tris, __ldg(ref_ids + cur));
             r.steps += 1 + (cell.end - cell.begin);
         }
@@ -366,41 +403,133 @@ __device__ __forceinline__ bool walk_warp(bool ok, RayState& r, const TraversalP
 // warp picks specialised for its direction octant when all its rays share one (walk_warp).
 // ---------------------------------------------------------------------------
 constexpr int kTileBlock = 128;
-constexpr int kTileBlocksPerSm = 10;     // <= 51 registers: 40 resident warps per SM, measured best of 8 / 10 / 12
+constexpr int kTileBlocksPerSm = HGB_TILE_BLOCKS;     // 10: <= 51 registers, 40 resident warps per SM, measured best of 8 / 10 / 12
 
-template <typename CellT, bool kPrimId>
+/// The scene's arrays as 128-byte lines, for the warm-up of the L2 at the start of a launch: callers (and
+/// bench.py's protocol) may have evicted the scene since the last frame, and a march that finds its voxel map,
+/// cells, references and triangles only through chains of dependent misses pays a DRAM latency per link. All
+/// threads of the launch request the lines once (prefetch.global.L2, no register, no wait), about one line per
+/// thread for a scene of 30 MB; scenes that do not fit the L2 comfortably are not requested (lines[] all zero).
+struct ScenePrefetch {
+    const char* base[4];
+    int lines[4];
+};
+
+__device__ __forceinline__ void warm_l2(const ScenePrefetch& S) {
+    const int stride = gridDim.x * blockDim.x;
+    const int me = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+        for (int line = me; line < S.lines[a]; line += stride)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(S.base[a] + size_t(line) * 128));
+}
+
+/// Tile hand-out without a reset: the counter only ever grows, the host passes the value it has at the start
+/// of the launch (`base`). Every traced tile is followed by exactly one fetch, so a launch over T tiles advances
+/// the counter by exactly T and the host knows the next base without reading anything back (uint32 wrap-around
+/// is harmless: only differences are used). Saves the memset node in front of every launch.
+__device__ __forceinline__ int fetch_tile(unsigned* __restrict__ next_tile, unsigned base, int first_dynamic, int lane) {
+    int tile = 0;
+    if (lane == 0) tile = first_dynamic + int(atomicAdd(next_tile, 1u) - base);
+    return __shfl_sync(0xFFFFFFFFu, tile, 0);
+}
+
+/// 16-byte asynchronous copy global -> shared that leaves no trace in L1 (cp.async.cg): the staging path of the
+/// next tile's rays. Each lane copies and later reads its own 32 bytes, so cp.async.wait_all is all the
+/// synchronisation there is.
+__device__ __forceinline__ void stage16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(unsigned(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+/// kAhead: 0 = tiles fetched on demand, 1 = next tile reserved early and its rays requested into L2 (prefetch.global.L2),
+/// 2 = next tile reserved early and its rays staged through shared memory (cp.async)
+#ifdef HGB_TILE_TRACE
+// Diagnosis build only (tools/gpu_tile_variants.py): per warp [first tile started, last tile finished, tiles traced], ns
+__device__ long long g_tile_trace[3 * 8192];
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
+template <typename CellT, bool kPrimId, int kAhead>
 __global__ void __launch_bounds__(kTileBlock, kTileBlocksPerSm)
 traverse_tiles(const __grid_constant__ TraversalParams P,
                const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
-               const int* __restrict__ layout, int host_width, int* __restrict__ next_tile, int* __restrict__ feedback) {
-    constexpr unsigned kAll = 0xFFFFFFFFu;
+               const int* __restrict__ layout, int host_width, unsigned* __restrict__ next_tile, unsigned ticket_base,
+               int* __restrict__ feedback, const __grid_constant__ ScenePrefetch scene) {
+    // kStage: while a tile is traced, the rays of the warp's next tile travel into shared memory (cp.async) and
+    // the fetch of the tile index after that is in flight: neither the atomic's round trip nor the HBM (or, for
+    // host-resident ray buffers, PCIe) latency of the ray loads sits between two tiles. Reserving a tile ahead
+    // lengthens the tail of the launch (an idle warp cannot take a tile another warp holds), so the last two
+    // rounds of tiles are fetched on demand as before.
+    constexpr bool kStage = kAhead == 2;
+    __shared__ float4 staged[kStage ? 2 * kTileBlock : 1];
     const int lane = threadIdx.x & 31;
     // feedback (device memory, may be null): [0] += warps whose rays did not share a direction octant, [1] += 1
     // per launch. A buffer of camera rays has a few such warps along the image axes; a buffer whose warps are
     // mostly mixed is not what this kernel is for: the host copies the words back now and then and moves such a
     // buffer to the incoherent kernel.
     if (feedback && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(feedback + 1, 1);
+    warm_l2(scene);
     const int width = layout ? __ldg(layout) : host_width;
     const int num_tiles = (num_rays + 31) >> 5;
     const int first_dynamic = gridDim.x * (kTileBlock / 32);
+    const int ahead_limit = num_tiles - 2 * first_dynamic;     // tiles below this index are traced with a successor in hand
     int tile = blockIdx.x * (kTileBlock / 32) + (threadIdx.x >> 5);
+    int next = -1;                                             // kStage: tile held in reserve (-1: none)
+    bool have_staged = false;
+#ifdef HGB_TILE_TRACE
+    const int trace_slot = blockIdx.x * (kTileBlock / 32) + (threadIdx.x >> 5);
+    int traced_tiles = 0;
+    if (lane == 0 && trace_slot < 8192) g_tile_trace[3 * trace_slot] = global_ns();
+#endif
     while (tile < num_tiles) {
-        int id = tile * 32 + lane;
-        const bool live = id < num_rays;
         RayState r;
         bool ok = false;
-        if (live) {
-            if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
-            ok = start_ray(r, P, rays, id);
+        {
+            int id = tile * 32 + lane;
+            if (id < num_rays) {
+                if (kStage && have_staged) {
+                    stage_wait();
+                    ok = init_ray(r, P, staged[2 * threadIdx.x], staged[2 * threadIdx.x + 1]);
+                } else {
+                    if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
+                    ok = start_ray(r, P, rays, id);
+                }
+            }
+        }
+        have_staged = false;
+        if (kAhead && tile < ahead_limit) {
+            next = fetch_tile(next_tile, ticket_base, first_dynamic, lane);
+            int nid = next * 32 + lane;
+            if (next < num_tiles && nid < num_rays) {
+                if (width > 0) nid = tiled_ray_index_nodiv(next, lane, width);
+                if (kStage) {
+                    stage16(&staged[2 * threadIdx.x], reinterpret_cast<const float4*>(rays + nid));
+                    stage16(&staged[2 * threadIdx.x + 1], reinterpret_cast<const float4*>(rays + nid) + 1);
+                    have_staged = true;
+                } else {
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(rays + nid));
+                }
+            }
         }
         const bool uniform = walk_warp(ok, r, P, entries, cells, ref_ids, tris);
         if (!uniform && feedback && lane == 0) atomicAdd(feedback, 1);
-        if (live) finish_ray<kPrimId>(r, hits, id);
+        {   // the ray's place in the buffer again (cheaper than keeping it in a register across the march)
+            int id = tile * 32 + lane;
+            if (id < num_rays) {
+                if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
+                finish_ray<kPrimId>(r, hits, id);
+            }
+        }
         __syncwarp();
-        if (lane == 0) tile = first_dynamic + atomicAdd(next_tile, 1);
-        tile = __shfl_sync(kAll, tile, 0);
+#ifdef HGB_TILE_TRACE
+        traced_tiles++;
+        if (lane == 0 && trace_slot < 8192) { g_tile_trace[3 * trace_slot + 1] = global_ns(); g_tile_trace[3 * trace_slot + 2] = traced_tiles; }
+#endif
+        if (kAhead && next >= 0) { tile = next; next = -1; }
+        else tile = fetch_tile(next_tile, ticket_base, first_dynamic, lane);
     }
 }
 
@@ -474,8 +603,7 @@ __global__ void __launch_bounds__(128, 10)
 render_tiles(const __grid_constant__ TraversalParams P, const __grid_constant__ FrameParams F,
              const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
              const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
-             unsigned* __restrict__ pixels, int* __restrict__ next_tile) {
-    constexpr unsigned kAll = 0xFFFFFFFFu;
+             unsigned* __restrict__ pixels, unsigned* __restrict__ next_tile, unsigned ticket_base) {
     const int lane = threadIdx.x & 31;
     const int num_pixels = F.width * F.height;
     const int num_tiles = (num_pixels + 31) >> 5;
@@ -496,8 +624,7 @@ render_tiles(const __grid_constant__ TraversalParams P, const __grid_constant__ 
         walk_warp(ok, r, P, entries, cells, ref_ids, tris);
         if (live) pixels[id] = shade_pixel<kMode>(r, F.clip);
         __syncwarp();
-        if (lane == 0) tile = first_dynamic + atomicAdd(next_tile, 1);
-        tile = __shfl_sync(kAll, tile, 0);
+        tile = fetch_tile(next_tile, ticket_base, first_dynamic, lane);
     }
 }
 
@@ -537,10 +664,11 @@ traverse_voting(const __grid_constant__ TraversalParams P,
                 const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                 const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                 const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
-                int* __restrict__ next_ray) {
+                int* __restrict__ next_ray, const int* __restrict__ layout, int host_width) {
     constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
     constexpr unsigned kAll = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
+    const int width = layout ? __ldg(layout) : host_width;      // > 0: rays are handed out in 8x4 tile order
 
     RayState r;
     int   ray_id = -1;          // -1: lane is idle
@@ -567,8 +695,9 @@ traverse_voting(const __grid_constant__ TraversalParams P,
         if (idle == kAll && drained) break;
         if (!drained && __popc(idle) >= kVoteRefillMinLanes) {
             if (ray_id < 0) {
-                const int id = pool + __popc(idle & ((1u << lane) - 1u));
+                int id = pool + __popc(idle & ((1u << lane) - 1u));
                 if (id < pool_end) {
+                    if (width > 0) id = tiled_ray_index(id, width);
                     if (start_ray(r, P, rays, id)) ray_id = id;
                     else finish_ray<kPrimId>(r, hits, id);
                 }
@@ -625,9 +754,19 @@ traverse_voting(const __grid_constant__ TraversalParams P,
     }
 }
 
-/// Per-device launch state.
+/// A tile counter in device memory and the value the host knows it to have (fetch_tile)
+struct Ticket {
+    unsigned* word = nullptr;
+    unsigned base = 0;
+};
+
+/// Per-device launch state. One host thread at a time per device (`lock`): the tickets and the buffer
+/// classification are host-side bookkeeping of what has been enqueued.
 struct DeviceState {
-    int* counter = nullptr;          // global ray counter of the persistent kernel
+    std::mutex lock;
+    int* words = nullptr;            // 256 bytes of device memory, one 32-byte sector per word in use (below)
+    int* vote_counter = nullptr;     // ray counter of the persistent voting kernel (reset before every launch)
+    Ticket tiles;                    // tile counter of traverse_tiles / render_tiles on the default stream
     int* layout = nullptr;           // [0] = raster width found by detect_raster (0 = none)
     int* layout_host = nullptr;      // pinned, mapped copy of layout[0]; -1 = detection still in flight
     const void* seen_rays = nullptr; // buffer the layout belongs to
@@ -646,23 +785,32 @@ struct DeviceState {
     cudaEvent_t  traced[kMaxChunks] = {};
     cudaEvent_t  stream_done[kStreams] = {};
     cudaEvent_t  frame_start = nullptr;
-    int* stream_counters = nullptr;  // ray counter of the persistent kernel, one per traversal stream (32-byte stride)
+    int* stream_vote_counters[2] = {};              // per traversal stream
+    Ticket stream_tiles[2];
 };
 
 DeviceState& device_state() {
     static DeviceState states[64];
+    static std::mutex init_lock;
     int dev = 0;
     HGB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) { std::fprintf(stderr, "hagrid_b200: device index out of range\n"); std::abort(); }
     DeviceState& st = states[dev];
-    if (!st.counter) {
-        HGB_CUDA(cudaMalloc(&st.counter, 128));
-        st.layout = st.counter + 16;
-        HGB_CUDA(cudaMemset(st.counter, 0, 128));
+    std::lock_guard<std::mutex> guard(init_lock);
+    if (!st.words) {
+        HGB_CUDA(cudaMalloc(&st.words, 256));
+        HGB_CUDA(cudaMemset(st.words, 0, 256));
+        st.vote_counter = st.words;
+        st.tiles.word = reinterpret_cast<unsigned*>(st.words + 8);
+        st.stream_vote_counters[0] = st.words + 16;
+        st.stream_tiles[0].word = reinterpret_cast<unsigned*>(st.words + 24);
+        st.stream_vote_counters[1] = st.words + 32;
+        st.stream_tiles[1].word = reinterpret_cast<unsigned*>(st.words + 40);
+        st.layout = st.words + 48;
+        st.feedback_dev = st.words + 56;
         HGB_CUDA(cudaHostAlloc(&st.layout_host, 4 * sizeof(int), cudaHostAllocMapped));
         st.layout_host[0] = st.layout_host[1] = st.layout_host[2] = st.layout_host[3] = 0;
         st.feedback_host = st.layout_host + 2;
-        st.feedback_dev = st.counter + 24;
         HGB_CUDA(cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     return st;
@@ -679,76 +827,106 @@ void prepare_streams(DeviceState& st) {
         HGB_CUDA(cudaEventCreateWithFlags(&st.traced[i], cudaEventDisableTiming));
     }
     HGB_CUDA(cudaEventCreateWithFlags(&st.frame_start, cudaEventDisableTiming));
-    HGB_CUDA(cudaMalloc(&st.stream_counters, 64));
 }
 
 // 0: per thread, buffer order   1: persistent warps, majority-scheduled   2: per thread, re-tiled when a raster is detected
 // 4: resident warps pulling tiles, re-tiled when a raster is detected
 // 3 (default): 4 for buffers that are (or may be) rasters, 1 once a buffer is known not to be one
-int g_variant = -1;
+std::atomic<int> g_variant{-1};
 
 // Host-buffer frames: rays per full-size chunk (tuned on B200/PCIe 5: ~350 K rays = 11 MB up, 5.6 MB down)
-int g_host_frame_chunk = 384 * 1024;
+std::atomic<int> g_host_frame_chunk{384 * 1024};
+// Host-buffer frames of page-locked raster buffers: 0 = staged through device buffers both ways, 1 = rays staged by the
+// copy engine, hits written by the kernel straight into the caller's host buffer, 2 = one launch that reads the rays
+// from and writes the hits to host memory (cp.async staging hides the PCIe latency)
+std::atomic<int> g_host_frame_mode{0};
+// Host-buffer frames: > 0 = every chunk is this percentage of the rays still to go, 0 = chunks of equal size
+std::atomic<int> g_host_frame_fraction{0};
+// traverse_tiles: stage the next tile's rays through shared memory while the current tile is traced
+std::atomic<int> g_tile_stage{0};
+// rasters smaller than this many rays are traced one thread per ray (re-tiled): a small launch does not fill the resident warps
+std::atomic<int> g_tile_min_rays{512 << 10};
 
 int traverse_variant() {
-    if (g_variant < 0) {
-        const char* v = std::getenv("HGB_TRAVERSE_VARIANT");
-        g_variant = v ? std::atoi(v) : 3;
+    int v = g_variant.load();
+    if (v < 0) {
+        const char* e = std::getenv("HGB_TRAVERSE_VARIANT");
+        v = e ? std::atoi(e) : 3;
+        g_variant.store(v);
     }
-    return g_variant;
+    return v;
 }
 
-/// Enqueues one traversal launch on `stream`: 1 = persistent voting warps, 4 = resident warps pulling tiles
-/// (both need `counter`), otherwise one thread per ray; 2 and 4 re-tile by the raster width in
+// Triangle arrays this library has been shown with their length (build_grid / expand_grid receive it, traverse_grid
+// does not): lets a launch request the triangles into L2 along with the grid.
+std::mutex g_tri_lock;
+std::unordered_map<const void*, int> g_tri_counts;
+
+// L2 warm-up at the start of a tile launch: scenes up to this many bytes (0 = never)
+std::atomic<int> g_scene_prefetch_mb{64};
+
+ScenePrefetch scene_prefetch(const Grid& grid, const void* cells, size_t cell_bytes, const Tri* tris) {
+    ScenePrefetch S = {};
+    int num_tris = 0;
+    {
+        std::lock_guard<std::mutex> guard(g_tri_lock);
+        auto it = g_tri_counts.find(tris);
+        if (it != g_tri_counts.end()) num_tris = it->second;
+    }
+    const size_t bytes[4] = {size_t(grid.num_entries) * 4, size_t(grid.num_cells) * cell_bytes, size_t(grid.num_refs) * 4, size_t(num_tris) * sizeof(Tri)};
+    const void* base[4] = {grid.entries, cells, grid.ref_ids, tris};
+    if (bytes[0] + bytes[1] + bytes[2] + bytes[3] > size_t(g_scene_prefetch_mb.load()) << 20) return S;
+    for (int a = 0; a < 4; a++) {
+        S.base[a] = static_cast<const char*>(base[a]);
+        S.lines[a] = int((bytes[a] + 127) / 128);
+    }
+    return S;
+}
+
+/// Enqueues one traversal launch on `stream`: 1 = persistent voting warps (needs `vote_counter`), 4 = resident
+/// warps pulling tiles (needs `ticket`), otherwise one thread per ray; 2 and 4 re-tile by the raster width in
 /// `layout[0]` (device) or `host_width`.
 template <typename CellT, bool kPrimId>
 void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays,
-             int variant, const int* layout, int host_width, int* counter, int num_sms, cudaStream_t stream,
+             int variant, const int* layout, int host_width, int* vote_counter, Ticket& ticket, int num_sms, cudaStream_t stream,
              int* feedback = nullptr) {
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
+    const TraversalParams P = params_of(grid);
     if (variant == 4) {
-        HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
         const int blocks = min(num_sms * kTileBlocksPerSm, round_div(num_rays, kTileBlock));
-        traverse_tiles<CellT, kPrimId><<<blocks, kTileBlock, 0, stream>>>(
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, counter, feedback); count_launch();
+        const int ahead = g_tile_stage.load();
+        const ScenePrefetch scene = scene_prefetch(grid, cells, sizeof(CellT), tris);
+        if (ahead == 2)
+            traverse_tiles<CellT, kPrimId, 2><<<blocks, kTileBlock, 0, stream>>>(
+                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback, scene);
+        else if (ahead == 1)
+            traverse_tiles<CellT, kPrimId, 1><<<blocks, kTileBlock, 0, stream>>>(
+                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback, scene);
+        else
+            traverse_tiles<CellT, kPrimId, 0><<<blocks, kTileBlock, 0, stream>>>(
+                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback, scene);
+        ticket.base += unsigned((num_rays + 31) >> 5);      // one fetch per traced tile (fetch_tile)
+        count_launch();
     } else if (variant == 1) {
-        HGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        HGB_CUDA(cudaMemsetAsync(vote_counter, 0, sizeof(int), stream));
         // every warp reserves two blocks of rays up front: no more warps than there are blocks
         const int blocks = max(1, min(num_sms * kVoteBlocksPerSm, round_div(num_rays, 2 * kVoteBlock * (kBlockThreads / 32))));
         traverse_voting<CellT, kPrimId><<<blocks, kBlockThreads, 0, stream>>>(
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, counter); count_launch();
+            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, vote_counter, layout, host_width); count_launch();
     } else {
         traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128, 0, stream>>>(
-            g_params, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width); count_launch();
-    }
-}
-
-/// The traversal constants live in this translation unit, like the reference's __constant__s
-/// (src/traverse.cu:7-12): tracing a grid other than the one last given to setup_traversal would walk
-/// it with foreign dimensions (possibly forever), so that caller error is fatal here.
-void require_setup(const Grid& grid) {
-    if (!g_params_set) {
-        std::fprintf(stderr, "hagrid_b200: traverse_grid called before setup_traversal\n");
-        std::abort();
-    }
-    const TraversalParams& P = g_params;
-    const bool same = P.shift == grid.shift && P.dims_x == (grid.dims.x << grid.shift) && P.dims_y == (grid.dims.y << grid.shift) &&
-                      P.dims_z == (grid.dims.z << grid.shift) && P.min_x == grid.bbox.min.x && P.min_y == grid.bbox.min.y &&
-                      P.min_z == grid.bbox.min.z && P.max_x == grid.bbox.max.x && P.max_y == grid.bbox.max.y && P.max_z == grid.bbox.max.z;
-    if (!same) {
-        std::fprintf(stderr, "hagrid_b200: traverse_grid called with a grid other than the one given to setup_traversal\n");
-        std::abort();
+            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width); count_launch();
     }
 }
 
 template <typename CellT, bool kPrimId>
 void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
     if (num_rays <= 0) return;
-    require_setup(grid);
     DeviceState& st = device_state();
+    std::lock_guard<std::mutex> guard(st.lock);
     int variant = traverse_variant();
     int* feedback = nullptr;
-    if (variant >= 2 && variant <= 4) {
+    if (variant >= 2 && variant <= 5) {
         // What kind of buffer is this? A new one (other address or size) is looked at on the device before its
         // first launch; the answer is remembered on the host.
         // A buffer known as a raster is not looked at again — the tile kernel reports when its contents stop
@@ -787,10 +965,9 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
             st.seen_count = num_rays;
         }
         if (variant == 3) {
-            // small buffers do not fill the resident-warp kernels (5 920 warps on 148 SMs) and the reset of their
-            // counter costs as much as the traversal: one thread per ray then (C1, 65 536 rays: 15.8 vs 18.2 us)
+            // small buffers do not fill the resident-warp kernels (5 920 warps on 148 SMs): one thread per ray then
             if (st.seen_class == 0) variant = num_rays < (128 << 10) ? 0 : 1;
-            else                    variant = num_rays < (512 << 10) ? 2 : 4;
+            else                    variant = num_rays < g_tile_min_rays.load() ? 2 : 4;
         }
         if (variant == 4 && st.seen_class > 0) {
             feedback = st.feedback_dev;
@@ -802,8 +979,10 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
             }
         }
     }
-    enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, (variant == 2 || variant == 4) ? st.layout : nullptr, 0,
-                            st.counter, st.num_sms, 0, feedback);
+    // 5 (experiment): the voting kernel handed rays in tile order
+    const bool tiled = variant == 2 || variant == 4 || variant == 5;
+    enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant == 5 ? 1 : variant, tiled ? st.layout : nullptr, 0,
+                            st.vote_counter, st.tiles, st.num_sms, 0, feedback);
     if (feedback) {
         // copied back after launches 1, 2, 4 and then every 8th: one 8-byte copy in eight launches
         const int tick = ++st.feedback_tick;
@@ -860,12 +1039,23 @@ int host_raster_width(const Ray* rays, int n) {
     return misses > kSpot / 16 ? 0 : width;
 }
 
+/// The address under which the device reaches a page-locked host buffer, or null for pageable memory
+template <typename T>
+T* device_alias(T* host) {
+    void* alias = nullptr;
+    if (cudaHostGetDevicePointer(&alias, const_cast<void*>(static_cast<const void*>(host)), 0) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return static_cast<T*>(alias);
+}
+
 template <typename CellT, bool kPrimId>
 void launch_host_frame(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* host_rays, Hit* host_hits,
                        int num_rays, Ray* dev_rays, Hit* dev_hits) {
     if (num_rays <= 0) return;
-    require_setup(grid);
     DeviceState& st = device_state();
+    std::lock_guard<std::mutex> guard(st.lock);
     prepare_streams(st);
 
     int variant = traverse_variant();
@@ -874,38 +1064,90 @@ void launch_host_frame(const Grid& grid, const CellT* cells, const Tri* tris, co
         width = host_raster_width(host_rays, num_rays);
         variant = width > 0 ? (variant == 2 ? 2 : 4) : (variant == 3 ? 1 : 0);
     }
-    // Chunks are whole 4-row tile bands of a raster, else whole blocks. Full-size chunks keep the copy
-    // engines busy with few, large transfers; the last one is split 1/2, 1/4, 1/4 because nothing
-    // overlaps the final traversal + download.
-    const int granule = width > 0 ? width * kTileH : kBlockThreads;
-    long long full = std::max<long long>(granule, (long long)round_div(g_host_frame_chunk, granule) * granule);
-    full = std::max<long long>(full, (long long)round_div(round_div(num_rays, DeviceState::kMaxChunks - 4), granule) * granule);
-    std::vector<int> sizes;
-    {
-        long long rest = num_rays;
-        while (rest > full + full / 2) { sizes.push_back(int(full)); rest -= full; }
-        const long long half = std::min<long long>(rest, (long long)round_div(int(rest / 2), granule) * granule);
-        const long long quarter = std::min<long long>(rest - half, (long long)round_div(int(rest / 4), granule) * granule);
-        if (half > 0) sizes.push_back(int(half));
-        if (quarter > 0) sizes.push_back(int(quarter));
-        if (rest - half - quarter > 0) sizes.push_back(int(rest - half - quarter));
-    }
+    // Page-locked raster frames: the kernel can write the hits into the caller's buffer itself (no download
+    // copies, no tail behind the last traversal), and read the rays from it as well
+    int mode = variant == 4 ? g_host_frame_mode.load() : 0;
+    const Ray* rays_alias = mode == 2 ? device_alias(host_rays) : nullptr;
+    Hit* hits_alias = mode >= 1 ? device_alias(host_hits) : nullptr;
+    if (mode >= 1 && !hits_alias) mode = 0;
+    if (mode == 2 && !rays_alias) mode = 1;
 
-    cudaStream_t up = st.streams[0], down = st.streams[1];
     HGB_CUDA(cudaEventRecord(st.frame_start, 0));           // frames are ordered after earlier default-stream work
     for (int i = 0; i < DeviceState::kStreams; i++) HGB_CUDA(cudaStreamWaitEvent(st.streams[i], st.frame_start, 0));
-    long long begin = 0;
-    for (size_t c = 0; c < sizes.size(); begin += sizes[c], c++) {
-        const int count = sizes[c];
-        cudaStream_t run = st.streams[2 + (c & 1)];      // consecutive traversals may overlap (tails of incoherent chunks)
-        HGB_CUDA(cudaMemcpyAsync(dev_rays + begin, host_rays + begin, sizeof(Ray) * size_t(count), cudaMemcpyHostToDevice, up));
-        HGB_CUDA(cudaEventRecord(st.uploaded[c], up));
-        HGB_CUDA(cudaStreamWaitEvent(run, st.uploaded[c], 0));
-        enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, dev_hits + begin, count, variant, nullptr, width,
-                                st.stream_counters + (c & 1) * 8, st.num_sms, run);
-        HGB_CUDA(cudaEventRecord(st.traced[c], run));
-        HGB_CUDA(cudaStreamWaitEvent(down, st.traced[c], 0));
-        HGB_CUDA(cudaMemcpyAsync(host_hits + begin, dev_hits + begin, sizeof(Hit) * size_t(count), cudaMemcpyDeviceToHost, down));
+    if (mode == 2) {
+        enqueue<CellT, kPrimId>(grid, cells, tris, rays_alias, hits_alias, num_rays, variant, nullptr, width,
+                                st.stream_vote_counters[0], st.stream_tiles[0], st.num_sms, st.streams[2]);
+    } else {
+        // Chunks are whole 4-row tile bands of a raster, else whole blocks. Full-size chunks keep the copy
+        // engines busy with few, large transfers; the last one is split 1/2, 1/4, 1/4 because nothing
+        // overlaps the final traversal (+ download).
+        const int granule = width > 0 ? width * kTileH : kBlockThreads;
+        const int chunk = g_host_frame_chunk.load();
+        std::vector<int> sizes;
+        const int fraction = g_host_frame_fraction.load();
+        if (fraction > 0) {
+            // Shrinking chunks: every chunk is `fraction` percent of what is left (never below `chunk` rays): few, large
+            // copies while there is plenty to overlap them with, small ones at the end where nothing hides the last
+            // traversal and download.
+            long long rest = num_rays;
+            while (rest > 0 && int(sizes.size()) < DeviceState::kMaxChunks - 1) {
+                long long want = std::max<long long>(chunk, rest * fraction / 100);
+                want = std::max<long long>(granule, (want + granule - 1) / granule * granule);
+                if (want > rest || rest - want < chunk / 2) want = rest;
+                sizes.push_back(int(want));
+                rest -= want;
+            }
+            if (rest > 0) sizes.push_back(int(rest));
+        } else {
+            long long full = std::max<long long>(granule, (long long)round_div(chunk, granule) * granule);
+            full = std::max<long long>(full, (long long)round_div(round_div(num_rays, DeviceState::kMaxChunks - 4), granule) * granule);
+            long long rest = num_rays;
+            while (rest > full + full / 2) { sizes.push_back(int(full)); rest -= full; }
+            const long long half = std::min<long long>(rest, (long long)round_div(int(rest / 2), granule) * granule);
+            const long long quarter = std::min<long long>(rest - half, (long long)round_div(int(rest / 4), granule) * granule);
+            if (half > 0) sizes.push_back(int(half));
+            if (quarter > 0) sizes.push_back(int(quarter));
+            if (rest - half - quarter > 0) sizes.push_back(int(rest - half - quarter));
+        }
+        cudaStream_t up = st.streams[0], down = st.streams[1];
+        // HGB_FRAME_TRACE=1: time stamps of every chunk's upload, traversal and download (diagnosis only)
+        static const bool trace = std::getenv("HGB_FRAME_TRACE") != nullptr;
+        std::vector<cudaEvent_t> stamps;
+        auto stamp = [&](cudaStream_t on) {
+            if (!trace) return;
+            cudaEvent_t e; HGB_CUDA(cudaEventCreate(&e)); HGB_CUDA(cudaEventRecord(e, on)); stamps.push_back(e);
+        };
+        stamp(up);
+        long long begin = 0;
+        for (size_t c = 0; c < sizes.size(); begin += sizes[c], c++) {
+            const int count = sizes[c];
+            cudaStream_t run = st.streams[2 + (c & 1)];      // consecutive traversals may overlap (tails of incoherent chunks)
+            HGB_CUDA(cudaMemcpyAsync(dev_rays + begin, host_rays + begin, sizeof(Ray) * size_t(count), cudaMemcpyHostToDevice, up));
+            HGB_CUDA(cudaEventRecord(st.uploaded[c], up));
+            stamp(up);
+            HGB_CUDA(cudaStreamWaitEvent(run, st.uploaded[c], 0));
+            // mode 3: only the last two chunks write their hits across PCIe themselves (nothing overlaps their download)
+            const bool direct = mode == 1 || (mode == 3 && c + 2 >= sizes.size());
+            enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, (direct ? hits_alias : dev_hits) + begin, count, variant, nullptr, width,
+                                    st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
+            stamp(run);
+            if (!direct) {
+                HGB_CUDA(cudaEventRecord(st.traced[c], run));
+                HGB_CUDA(cudaStreamWaitEvent(down, st.traced[c], 0));
+                HGB_CUDA(cudaMemcpyAsync(host_hits + begin, dev_hits + begin, sizeof(Hit) * size_t(count), cudaMemcpyDeviceToHost, down));
+            }
+            stamp(down);
+        }
+        if (trace) {
+            HGB_CUDA(cudaDeviceSynchronize());
+            std::fprintf(stderr, "frame trace (ms since the first upload was enqueued): chunk rays uploaded traced downloaded\n");
+            for (size_t c = 0; c < sizes.size(); c++) {
+                float t[3];
+                for (int k = 0; k < 3; k++) HGB_CUDA(cudaEventElapsedTime(&t[k], stamps[0], stamps[1 + 3 * c + k]));
+                std::fprintf(stderr, "  %2zu %8d %7.3f %7.3f %7.3f\n", c, sizes[c], t[0], t[1], t[2]);
+            }
+            for (cudaEvent_t e : stamps) cudaEventDestroy(e);
+        }
     }
     HGB_CUDA(cudaGetLastError());
     for (int i = 0; i < DeviceState::kStreams; i++) {
@@ -923,21 +1165,18 @@ void dispatch(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int
 
 } // namespace
 
+void note_triangle_array(const Tri* tris, int num_tris) {
+    std::lock_guard<std::mutex> guard(g_tri_lock);
+    if (g_tri_counts.size() > 4096) g_tri_counts.clear();       // addresses are reused; the map is a hint, not a registry
+    g_tri_counts[tris] = num_tris;
+}
+
 void setup_traversal(const Grid& grid) {
-    // Host IEEE arithmetic, same expressions as src/traverse.cu:97-101.
-    const vec3 extents = grid.bbox.extents();
-    const ivec3 dims = grid.dims << grid.shift;
-    const vec3 inv = vec3(dims) / extents;
-    const vec3 cell = extents / vec3(dims);
-    TraversalParams& P = g_params;
-    P.dims_x = dims.x; P.dims_y = dims.y; P.dims_z = dims.z;
-    P.top_x = dims.x >> grid.shift; P.top_y = dims.y >> grid.shift;
-    P.shift = grid.shift;
-    P.min_x = grid.bbox.min.x; P.min_y = grid.bbox.min.y; P.min_z = grid.bbox.min.z;
-    P.max_x = grid.bbox.max.x; P.max_y = grid.bbox.max.y; P.max_z = grid.bbox.max.z;
-    P.cell_x = cell.x; P.cell_y = cell.y; P.cell_z = cell.z;
-    P.inv_x = inv.x; P.inv_y = inv.y; P.inv_z = inv.z;
-    g_params_set = true;
+    // Nothing to capture: the constants the reference stores in __constant__ memory here (src/traverse.cu:97-108)
+    // are derived from the grid at every launch (params_of). The call creates the per-device launch state, so
+    // that the first traverse_grid does not pay for it.
+    (void)grid;
+    device_state();
 }
 
 namespace {
@@ -955,13 +1194,16 @@ FrameParams frame_params(const FrameCamera& cam, float clip, int width, int heig
 template <typename CellT>
 void launch_frame(const Grid& grid, const CellT* cells, const Tri* tris, const FrameParams& F, int mode, unsigned* pixels) {
     DeviceState& st = device_state();
+    std::lock_guard<std::mutex> guard(st.lock);
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
+    const TraversalParams P = params_of(grid);
     const int num_pixels = F.width * F.height;
-    HGB_CUDA(cudaMemsetAsync(st.counter, 0, sizeof(int), 0));
     const int blocks = std::min(st.num_sms * 10, round_div(num_pixels, 128));
-    if (mode == 0)      render_tiles<CellT, 0><<<blocks, 128>>>(g_params, F, entries, cells, grid.ref_ids, tris, pixels, st.counter);
-    else if (mode == 1) render_tiles<CellT, 1><<<blocks, 128>>>(g_params, F, entries, cells, grid.ref_ids, tris, pixels, st.counter);
-    else                render_tiles<CellT, 2><<<blocks, 128>>>(g_params, F, entries, cells, grid.ref_ids, tris, pixels, st.counter);
+    Ticket& t = st.tiles;
+    if (mode == 0)      render_tiles<CellT, 0><<<blocks, 128>>>(P, F, entries, cells, grid.ref_ids, tris, pixels, t.word, t.base);
+    else if (mode == 1) render_tiles<CellT, 1><<<blocks, 128>>>(P, F, entries, cells, grid.ref_ids, tris, pixels, t.word, t.base);
+    else                render_tiles<CellT, 2><<<blocks, 128>>>(P, F, entries, cells, grid.ref_ids, tris, pixels, t.word, t.base);
+    t.base += unsigned((num_pixels + 31) >> 5);
     count_launch();
     HGB_CUDA(cudaGetLastError());
 }
@@ -989,15 +1231,19 @@ void generate_rays(const FrameCamera& cam, float clip, int width, int height, Ra
 void render_frame(const Grid& grid, const Tri* tris, const FrameCamera& cam, float clip, int width, int height,
                   int mode, unsigned* pixels) {
     if (width <= 0 || height <= 0) return;
-    require_setup(grid);
     const FrameParams F = frame_params(cam, clip, width, height);
     if (grid.small_cells) launch_frame<SmallCell>(grid, grid.small_cells, tris, F, mode, pixels);
     else                  launch_frame<Cell>(grid, grid.cells, tris, F, mode, pixels);
 }
 
 bool set_traversal_option(const char* key, int value) {
-    if (!std::strcmp(key, "traverse_variant")) { g_variant = value; return true; }
-    if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk = value > 0 ? value : 384 * 1024; return true; }
+    if (!std::strcmp(key, "traverse_variant")) { g_variant.store(value); return true; }
+    if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk.store(value > 0 ? value : 384 * 1024); return true; }
+    if (!std::strcmp(key, "host_frame_mode")) { g_host_frame_mode.store(value < 0 || value > 3 ? 0 : value); return true; }
+    if (!std::strcmp(key, "host_frame_fraction")) { g_host_frame_fraction.store(value < 0 || value > 90 ? 0 : value); return true; }
+    if (!std::strcmp(key, "tile_stage")) { g_tile_stage.store(value < 0 || value > 2 ? 0 : value); return true; }
+    if (!std::strcmp(key, "scene_prefetch_mb")) { g_scene_prefetch_mb.store(value < 0 ? 64 : value); return true; }
+    if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (512 << 10)); return true; }
     return false;
 }
 
@@ -1021,3 +1267,9 @@ void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays,
 }
 
 } // namespace hagrid
+
+#ifdef HGB_TILE_TRACE
+extern "C" __attribute__((visibility("default"))) int hgb_debug_tile_trace(long long* out) {
+    return cudaMemcpyFromSymbol(out, hagrid::g_tile_trace, sizeof(long long) * 3 * 8192) == cudaSuccess ? 0 : -1;
+}
+#endif

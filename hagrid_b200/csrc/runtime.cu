@@ -9,8 +9,8 @@
 
 namespace hagrid {
 
-unsigned long long g_kernel_launches = 0;
-unsigned long long kernel_launch_count() { return g_kernel_launches; }
+std::atomic<unsigned long long> g_kernel_launches{0};
+unsigned long long kernel_launch_count() { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 namespace {
 
@@ -36,6 +36,17 @@ void release(Slot& slot) {
 }
 
 } // namespace
+
+MemManager::~MemManager() {
+    // Idle and handed-out slots alike: the manager owns them all. Errors are ignored (a manager with static
+    // storage duration may be destroyed after the CUDA runtime has shut down).
+    for (Slot& slot : slots_) {
+        if (slot.ptr) cudaFreeAsync(slot.ptr, 0);
+        slot.ptr = nullptr;
+        slot.size = 0;
+    }
+    cudaGetLastError();
+}
 
 void MemManager::alloc_slot(Slot& slot, size_t bytes) {
     if (slot.in_use) {
@@ -90,6 +101,15 @@ void MemManager::debug_slots() const {
         total += slot.size;
     }
     std::cout << double(total) / (1024.0 * 1024.0) << "MB total" << std::endl;
+}
+
+/// Hands memory the stream-ordered pool retains back to the driver (after a scene has been destroyed)
+void trim_device_pool() {
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess || cudaMemPoolTrimTo(pool, 0) != cudaSuccess)
+        cudaGetLastError();
 }
 
 float profile(std::function<void()> work) {

@@ -1,6 +1,7 @@
 // Internal runtime helpers shared by the kernels' host code.
 #pragma once
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -17,8 +18,13 @@ inline void check_cuda(cudaError_t err, const char* what, const char* file, int 
 
 /// Number of kernels this library has launched since it was loaded (bench.py reports
 /// the count inside its timed region as `gpu_launches`).
-extern unsigned long long g_kernel_launches;
-inline void count_launch(int n = 1) { g_kernel_launches += (unsigned long long)n; }
+extern std::atomic<unsigned long long> g_kernel_launches;
+inline void count_launch(int n = 1) { g_kernel_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+struct Tri;
+/// Tells the traversal how long a device triangle array is (build_grid and the C ABI know, traverse_grid's
+/// signature does not say): used to request the triangles into L2 at the start of a launch.
+void note_triangle_array(const Tri* tris, int num_tris);
 
 } // namespace hagrid
 

@@ -39,6 +39,13 @@ class MemManager {
 public:
     explicit MemManager(bool keep = false) : usage_(0), max_usage_(0), keep_(keep) {}
 
+    /// Returns the memory of every slot to the device's pool (the reference has no destructor and leaks what keep
+    /// mode retained, src/mem_manager.h:34-42). Non-virtual, defined in the library: the object layout is unchanged.
+    /// The device the buffers live on must be current.
+    ~MemManager();
+    MemManager(const MemManager&) = delete;
+    MemManager& operator=(const MemManager&) = delete;
+
     /// Device buffer of n elements of T (uninitialised)
     template <typename T>
     HOST T* alloc(size_t n) {

@@ -215,6 +215,95 @@ def test_c3_compressed_grid_gives_same_hits(lib, sponza):
     sc2.close()
 
 
+def _bit_equal(got, want):
+    return np.array_equal(got["id"], want["id"]) and np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+
+
+@pytest.fixture(scope="module")
+def sponza_reference(ref_lib):
+    """The reference's own grid of the bench scene (C2 flags) and its hits for the bench's ray buffers."""
+    tris = scenes.sponza262k()
+    sc = Scene(tris, lib=ref_lib)
+    sc.build_all(0.15, 3.0, 0.995, 3, compress=False)
+    sc.setup_traversal()
+    plain = dump(sc)
+    views = {"default": scenes.default_view(tris), "long": scenes.default_view(tris, along_long_axis=True)}
+    want = {k: (sc.trace(v, HIT_PRIM_ID), sc.trace(v, HIT_STEPS)) for k, v in views.items()}
+    random = scenes.random_rays(tris, 1 << 22)
+    want_random_plain = sc.trace(random, HIT_PRIM_ID)
+    assert sc.compress_grid()
+    sc.setup_traversal()
+    small = dump(sc)
+    want_random = (sc.trace(random, HIT_PRIM_ID), sc.trace(random, HIT_STEPS))
+    sc.close()
+    return {"tris": tris, "plain": plain, "small": small, "views": views, "want": want, "random": random,
+            "want_random": want_random, "want_random_plain": want_random_plain}
+
+
+def test_c2_headline_buffers_match_the_reference_in_every_variant(lib, sponza, sponza_reference):
+    """BASELINE.json C2, the exact buffers bench.py times: grid byte-identical to the reference's, prim ids, t and step
+    counts bit-identical for the default view and the long-axis view, in all five kernel selections and with the
+    tile kernel's ray staging on and off."""
+    tris, sc, _ = sponza
+    R = sponza_reference
+    info, arrays = dump(sc)
+    assert grid_diff(info, arrays, (R["plain"][0],) + R["plain"][1]) == []
+    try:
+        for name, rays in R["views"].items():
+            want_ids, want_steps = R["want"][name]
+            assert (want_ids["id"] >= 0).mean() > 0.9
+            for v in VARIANTS:
+                for stage in ((0, 1) if v in (3, 4) else (1,)):
+                    lib.set_option("traverse_variant", v); lib.set_option("tile_stage", stage)
+                    assert _bit_equal(sc.trace(rays, HIT_PRIM_ID), want_ids), (name, v, stage)
+                    assert _bit_equal(sc.trace(rays, HIT_STEPS), want_steps), (name, v, stage)
+    finally:
+        lib.set_option("traverse_variant", 3); lib.set_option("tile_stage", 1)
+
+
+def test_c2_host_buffer_frames_match_the_reference_in_every_mode(lib, sponza, sponza_reference):
+    """The e2e call of bench.py (hgb_traverse_grid_host) with page-locked and pageable buffers, every frame mode."""
+    import torch
+    tris, sc, _ = sponza
+    rays = sponza_reference["views"]["default"]
+    want = sponza_reference["want"]["default"][0]
+    n = rays.shape[0]
+    pinned_rays = torch.from_numpy(rays.view(np.float32).reshape(n, 8)).pin_memory()
+    pinned_hits = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    try:
+        for mode in (0, 1, 2):
+            for stage in (0, 1):
+                lib.set_option("host_frame_mode", mode); lib.set_option("tile_stage", stage)
+                pinned_hits.zero_()
+                lib.check(lib.dll.hgb_traverse_grid_host(sc._h, pinned_rays.data_ptr(), pinned_hits.data_ptr(), n, HIT_PRIM_ID), "frame")
+                got = pinned_hits.numpy().view(want.dtype).reshape(-1)
+                assert _bit_equal(got, want), (mode, stage)
+                assert _bit_equal(sc.traverse_host(rays, HIT_PRIM_ID), want), ("pageable", mode, stage)
+    finally:
+        lib.set_option("host_frame_mode", 0); lib.set_option("tile_stage", 1)
+
+
+def test_c3_headline_buffer_matches_the_reference_in_every_variant(lib, sponza, sponza_reference):
+    """BASELINE.json C3: 4 194 304 random rays on the compressed grid (and on the plain one), all kernel selections."""
+    tris, sc, _ = sponza
+    R = sponza_reference
+    rays = R["random"]
+    sc2 = Scene(tris, lib=lib)
+    sc2.build_all(0.15, 3.0, 0.995, 3, compress=True)
+    info, arrays = dump(sc2)
+    assert grid_diff(info, arrays, (R["small"][0],) + R["small"][1]) == []
+    sc2.setup_traversal()
+    try:
+        for v in VARIANTS:
+            lib.set_option("traverse_variant", v)
+            assert _bit_equal(sc2.trace(rays, HIT_PRIM_ID), R["want_random"][0]), v
+            assert _bit_equal(sc2.trace(rays, HIT_STEPS), R["want_random"][1]), v
+            assert _bit_equal(sc.trace(rays, HIT_PRIM_ID), R["want_random_plain"]), v     # no new setup call: per-scene state
+    finally:
+        lib.set_option("traverse_variant", 3)
+    sc2.close()
+
+
 def _same_grid_as_reference(lib, ref_lib, tris, td, sd, compress=False):
     a, b = Scene(tris, keep_alive=True, lib=ref_lib), Scene(tris, keep_alive=True, lib=lib)
     a.build_all(td, sd, 0.995, 3, compress); b.build_all(td, sd, 0.995, 3, compress)
@@ -480,8 +569,9 @@ def test_a_reused_ray_buffer_may_change_its_character(lib, sponza):
 
 
 def test_tracing_a_grid_without_its_setup_is_an_error(lib):
-    """The traversal constants are per process (src/traverse.cu:7-12); the C ABI refuses to walk a grid
-    with another grid's constants instead of letting the kernel run wild."""
+    """hgb_setup_traversal must follow every change of a scene's grid (the reference's call order,
+    src/main.cpp:536-549; its constants are per process, src/traverse.cu:7-12): the C ABI refuses to trace a
+    scene whose setup is missing or stale."""
     from hagrid_b200 import HagridError
     g = Golden("cornell32")
     a, b = Scene(g.tris, lib=lib), Scene(scenes.small_mixed(500, seed=2), lib=lib)
@@ -496,6 +586,79 @@ def test_tracing_a_grid_without_its_setup_is_an_error(lib):
     a.setup_traversal()
     assert np.array_equal(a.trace(g.rays, HIT_PRIM_ID)["id"], g.hits["hits_cell_ids"]["id"])
     a.close(); b.close()
+
+
+def test_scenes_are_independent_of_each_other(lib):
+    """Traversal state is per scene: two scenes, set up once each, traced in turn (and from two host threads)
+    without another hgb_setup_traversal; on a box with two GPUs the second scene lives on the other device."""
+    import threading
+    g = Golden("cornell32")
+    other = scenes.small_mixed(20000, seed=5)
+    second_device = 1 if lib.device_count() > 1 else 0
+    a, b = Scene(g.tris, lib=lib), Scene(other, device=second_device, lib=lib)
+    a.build_all(g.top_density, g.snd_density); b.build_all(0.15, 3.0)
+    a.setup_traversal(); b.setup_traversal()
+    rays_b = scenes.random_rays(other, 300000, seed=3)
+    want_a, want_b = a.trace(g.rays, HIT_PRIM_ID), b.trace(rays_b, HIT_PRIM_ID)
+    assert np.array_equal(want_a["id"], g.hits["hits_cell_ids"]["id"])
+    for _ in range(3):
+        assert _bit_equal(a.trace(g.rays, HIT_PRIM_ID), want_a)
+        assert _bit_equal(b.trace(rays_b, HIT_PRIM_ID), want_b)
+    failures = []
+
+    def worker(sc, rays, want):
+        for _ in range(20):
+            if not _bit_equal(sc.trace(rays, HIT_PRIM_ID), want):
+                failures.append(sc)
+    threads = [threading.Thread(target=worker, args=(a, g.rays, want_a)), threading.Thread(target=worker, args=(b, rays_b, want_b))]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    assert not failures
+    a.close(); b.close()
+
+
+def test_new_triangles_invalidate_the_setup(lib):
+    """hgb_scene_set_tris replaces the array the grid's references index: tracing before a rebuild is an error."""
+    from hagrid_b200 import HagridError
+    g = Golden("cornell32")
+    sc = Scene(g.tris, lib=lib)
+    sc.build_all(g.top_density, g.snd_density); sc.setup_traversal()
+    sc.set_tris(g.tris[:8])
+    with pytest.raises(HagridError):
+        sc.trace(g.rays, HIT_PRIM_ID)
+    sc.set_tris(g.tris)
+    sc.build_all(g.top_density, g.snd_density); sc.setup_traversal()
+    assert np.array_equal(sc.trace(g.rays, HIT_PRIM_ID)["id"], g.hits["hits_cell_ids"]["id"])
+    sc.close()
+
+
+def test_grid_upload_rejects_bad_headers_and_keeps_the_old_grid(lib):
+    from hagrid_b200 import HagridError
+    g = Golden("cornell32")
+    sc = Scene(g.tris, lib=lib)
+    sc.build_all(g.top_density, g.snd_density); sc.setup_traversal()
+    info, e, c, r = g.stage["expand"]
+    for key, bad in (("num_cells", -1), ("num_entries", 0), ("num_refs", -5), ("shift", 99), ("dims", [0, 1, 1])):
+        d = dict(info); d[key] = bad
+        gi = info_from_dict(d)
+        with pytest.raises(HagridError):
+            lib.check(lib.dll.hgb_grid_upload(sc._h, gi, e.ctypes.data, c.ctypes.data, r.ctypes.data), "grid_upload")
+    assert np.array_equal(sc.trace(g.rays, HIT_PRIM_ID)["id"], g.hits["hits_cell_ids"]["id"])     # untouched
+    sc.close()
+
+
+def test_destroying_a_keep_alive_scene_returns_its_memory(lib):
+    """keep-alive slots used to stay allocated after hgb_scene_destroy."""
+    import torch
+    tris = scenes.hairball(200000, seed=3)
+    free0 = torch.cuda.mem_get_info(0)[0]
+    for _ in range(3):
+        sc = Scene(tris, keep_alive=True, lib=lib)
+        sc.build_all(0.12, 2.4, warmup=1, iters=2)
+        assert sc.peak_bytes() > 50 << 20
+        sc.close()
+    free1 = torch.cuda.mem_get_info(0)[0]
+    assert free0 - free1 < 32 << 20, (free0, free1)
 
 
 def test_buffer_pool_reuse(lib):
