@@ -48,7 +48,6 @@ void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays,
 bool set_traversal_option(const char* key, int value);
 unsigned long long kernel_launch_count();
 void trim_device_pool();
-void note_triangle_array(const Tri* tris, int num_tris);
 #endif
 }
 
@@ -609,9 +608,6 @@ int hgb_grid_upload(hgb_scene* s, const hgb_grid_info* info,
     g.num_entries = info->num_entries;
     g.num_refs = info->num_refs;
     g.offsets.assign(info->offsets, info->offsets + info->num_offsets);
-#ifndef HGB_REFERENCE_BUILD
-    if (s->tris) note_triangle_array(s->tris, s->num_tris);
-#endif
 
     g.entries = s->mem.alloc<Entry>(g.num_entries);
     s->mem.copy<Copy::HST_TO_DEV>(g.entries, static_cast<const Entry*>(host_entries), g.num_entries);

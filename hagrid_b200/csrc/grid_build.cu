@@ -430,7 +430,6 @@ struct Level {
 } // namespace
 
 void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, float top_density, float snd_density) {
-    note_triangle_array(tris, num_tris);
     // ---- scene box (one 24-byte copy back: the top-level resolution is host arithmetic)
     int* totals = mem.alloc<int>(16);
     unsigned* box_bits = reinterpret_cast<unsigned*>(totals) + 8;

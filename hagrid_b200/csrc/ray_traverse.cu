@@ -25,7 +25,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
-#include <unordered_map>
 #include <vector>
 
 #include "device_math.cuh"
@@ -37,7 +36,7 @@
 #define HGB_TILE_BLOCKS 10
 #endif
 #ifndef HGB_REF_UNROLL
-#define HGB_REF_UNROLL 0                 // 0: ptxas decides (it unrolls four-fold)
+#define HGB_REF_UNROLL 1                 // 0: ptxas decides (it unrolls four-fold)
 #endif
 #define HGB_STR2(x) #x
 #define HGB_STR(x) HGB_STR2(x)
@@ -92,6 +91,7 @@ struct RayState {
     int   hit_id;
     int   steps;
     int   vx, vy, vz;                   // current voxel
+    float tlast;                        // where the march stood when it was interrupted (walk with a step budget)
 };
 
 /// Ray/triangle test, expression shapes as in the reference SASS:
@@ -303,30 +303,45 @@ __device__ __forceinline__ int tiled_ray_index_nodiv(int tile, int lane, int wid
     return (ty * kTileH + (lane >> 3)) * width + tx * kTileW + (lane & 7);
 }
 
-/// The march of one ray through the grid after init_ray (src/traverse.cu:56-90)
+/// One cell of the march (src/traverse.cu:57-88): enter it, test its references in array order, count the steps.
+/// Returns the exit distance; the ray's voxel already is the next cell's.
 template <typename CellT, int kOct = -1>
-__device__ __forceinline__ void walk(RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
-                                     const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
-                                     const Tri* __restrict__ tris) {
+__device__ __forceinline__ float visit_cell(RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
+                                            const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
+                                            const Tri* __restrict__ tris) {
     constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
+    dev::CellBox cell;
+    const float texit = enter_cell<CellT, kOct>(r, P, entries, cells, cell);
+    // plain loops (HGB_REF_LOOP_PRAGMA: not unrolled, which keeps the tile kernel at 40 registers = 48 warps per SM)
+    if (kSentinel) {
+        int cur = cell.begin;
+        if (cur >= 0)
+            for (int ref = __ldg(ref_ids + cur++); ref >= 0; ref = __ldg(ref_ids + cur++)) intersect_tri(r, tris, ref);
+        r.steps += 1 + (cur - cell.begin);
+    } else {
+        HGB_REF_LOOP_PRAGMA
+        for (int cur = cell.begin; cur < cell.end; cur++) intersect_tri(r, tris, __ldg(ref_ids + cur));
+        r.steps += 1 + (cell.end - cell.begin);
+    }
+    return texit;
+}
+
+__device__ __forceinline__ bool left_grid(const RayState& r, const TraversalParams& P) {
+    // unsigned compares fold the < 0 tests
+    return (unsigned(r.vx) >= unsigned(P.dims_x)) | (unsigned(r.vy) >= unsigned(P.dims_y)) | (unsigned(r.vz) >= unsigned(P.dims_z));
+}
+
+/// The march of one ray through the grid after init_ray (src/traverse.cu:56-90). kBudget: the march is interrupted
+/// (returns false, r.tlast = where it stands) once the ray has taken `limit` steps; it continues with the next call.
+template <typename CellT, int kOct = -1, bool kBudget = false>
+__device__ __forceinline__ bool walk(RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
+                                     const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
+                                     const Tri* __restrict__ tris, int limit = 0) {
     while (true) {
-        dev::CellBox cell;
-        const float texit = enter_cell<CellT, kOct>(r, P, entries, cells, cell);
-        // plain loops: ptxas unrolls them four-fold and issues the loads of four triangles together, which
-        // measured faster than fetching the next reference one iteration ahead by hand
-        if (kSentinel) {
-            int cur = cell.begin;
-            if (cur >= 0)
-                for (int ref = __ldg(ref_ids + cur++); ref >= 0; ref = __ldg(ref_ids + cur++)) intersect_tri(r, tris, ref);
-            r.steps += 1 + (cur - cell.begin);
-        } else {
-            HGB_REF_LOOP_PRAGMA
-            for (int cur = cell.begin; cur < cell.end; cur++) intersect_tri(r, tris, __ldg(ref_ids + cur));
-            r.steps += 1 + (cell.end - cell.begin);
-        }
-        if (r.hit_t <= texit) break;
-        // left the grid? (unsigned compare folds the < 0 test)
-        if ((unsigned(r.vx) >= unsigned(P.dims_x)) | (unsigned(r.vy) >= unsigned(P.dims_y)) | (unsigned(r.vz) >= unsigned(P.dims_z))) break;
+        const float texit = visit_cell<CellT, kOct>(r, P, entries, cells, ref_ids, tris);
+        if (r.hit_t <= texit) return true;
+        if (left_grid(r, P)) return true;
+        if (kBudget && r.steps >= limit) { r.tlast = texit; return false; }
     }
 }
 
@@ -367,11 +382,12 @@ __device__ __forceinline__ int octant_of(const RayState& r) {
 
 /// March of the lanes with `ok` set. Called by all 32 lanes of a converged warp: when every marching lane has
 /// the same direction octant — the rule for an 8x4 tile of camera rays — the warp takes the loop specialised
-/// for it, otherwise the generic one. Same cells, same triangles, same order either way.
-template <typename CellT>
-__device__ __forceinline__ bool walk_warp(bool ok, RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
+/// for it, otherwise the generic one. Same cells, same triangles, same order either way. kBudget: lanes whose
+/// ray is not finished after `limit` steps come back with `ok` still set.
+template <typename CellT, bool kBudget = false>
+__device__ __forceinline__ bool walk_warp(bool& ok, RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
                                           const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
-                                          const Tri* __restrict__ tris) {
+                                          const Tri* __restrict__ tris, int limit = 0) {
     constexpr unsigned kAll = 0xFFFFFFFFu;
     const unsigned marching = __ballot_sync(kAll, ok);
     if (marching == 0) return true;
@@ -379,20 +395,22 @@ __device__ __forceinline__ bool walk_warp(bool ok, RayState& r, const TraversalP
     const int first = __shfl_sync(kAll, oct, __ffs(marching) - 1);
     const bool uniform = __all_sync(kAll, !ok || oct == first);
     if (!ok) return uniform;
+    bool done;
     if (uniform) {
         switch (first) {
-            case 0: walk<CellT, 0>(r, P, entries, cells, ref_ids, tris); break;
-            case 1: walk<CellT, 1>(r, P, entries, cells, ref_ids, tris); break;
-            case 2: walk<CellT, 2>(r, P, entries, cells, ref_ids, tris); break;
-            case 3: walk<CellT, 3>(r, P, entries, cells, ref_ids, tris); break;
-            case 4: walk<CellT, 4>(r, P, entries, cells, ref_ids, tris); break;
-            case 5: walk<CellT, 5>(r, P, entries, cells, ref_ids, tris); break;
-            case 6: walk<CellT, 6>(r, P, entries, cells, ref_ids, tris); break;
-            default: walk<CellT, 7>(r, P, entries, cells, ref_ids, tris); break;
+            case 0: done = walk<CellT, 0, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
+            case 1: done = walk<CellT, 1, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
+            case 2: done = walk<CellT, 2, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
+            case 3: done = walk<CellT, 3, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
+            case 4: done = walk<CellT, 4, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
+            case 5: done = walk<CellT, 5, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
+            case 6: done = walk<CellT, 6, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
+            default: done = walk<CellT, 7, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
         }
     } else {
-        walk<CellT, -1>(r, P, entries, cells, ref_ids, tris);
+        done = walk<CellT, -1, kBudget>(r, P, entries, cells, ref_ids, tris, limit);
     }
+    ok = !done;
     return uniform;
 }
 
@@ -405,131 +423,346 @@ __device__ __forceinline__ bool walk_warp(bool ok, RayState& r, const TraversalP
 constexpr int kTileBlock = 128;
 constexpr int kTileBlocksPerSm = HGB_TILE_BLOCKS;     // 10: <= 51 registers, 40 resident warps per SM, measured best of 8 / 10 / 12
 
-/// The scene's arrays as 128-byte lines, for the warm-up of the L2 at the start of a launch: callers (and
-/// bench.py's protocol) may have evicted the scene since the last frame, and a march that finds its voxel map,
-/// cells, references and triangles only through chains of dependent misses pays a DRAM latency per link. All
-/// threads of the launch request the lines once (prefetch.global.L2, no register, no wait), about one line per
-/// thread for a scene of 30 MB; scenes that do not fit the L2 comfortably are not requested (lines[] all zero).
-struct ScenePrefetch {
-    const char* base[4];
-    int lines[4];
-};
-
-__device__ __forceinline__ void warm_l2(const ScenePrefetch& S) {
-    const int stride = gridDim.x * blockDim.x;
-    const int me = blockIdx.x * blockDim.x + threadIdx.x;
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-        for (int line = me; line < S.lines[a]; line += stride)
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(S.base[a] + size_t(line) * 128));
-}
-
 /// Tile hand-out without a reset: the counter only ever grows, the host passes the value it has at the start
 /// of the launch (`base`). Every traced tile is followed by exactly one fetch, so a launch over T tiles advances
 /// the counter by exactly T and the host knows the next base without reading anything back (uint32 wrap-around
-/// is harmless: only differences are used). Saves the memset node in front of every launch.
+/// is harmless: only differences are used).
 __device__ __forceinline__ int fetch_tile(unsigned* __restrict__ next_tile, unsigned base, int first_dynamic, int lane) {
     int tile = 0;
     if (lane == 0) tile = first_dynamic + int(atomicAdd(next_tile, 1u) - base);
     return __shfl_sync(0xFFFFFFFFu, tile, 0);
 }
 
-/// 16-byte asynchronous copy global -> shared that leaves no trace in L1 (cp.async.cg): the staging path of the
-/// next tile's rays. Each lane copies and later reads its own 32 bytes, so cp.async.wait_all is all the
-/// synchronisation there is.
-__device__ __forceinline__ void stage16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(unsigned(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-/// kAhead: 0 = tiles fetched on demand, 1 = next tile reserved early and its rays requested into L2 (prefetch.global.L2),
-/// 2 = next tile reserved early and its rays staged through shared memory (cp.async)
+// ---------------------------------------------------------------------------
+// Split march of a straggler. A tile is done when its longest ray is done, a launch when its longest tile is: on the
+// 7.8 M-triangle scene the mean ray takes 8 steps, the longest 347 (155 cells), and that one ray -- a chain of
+// dependent L2 round trips, cell after cell -- lasts as long as the rest of the frame together (the queue of tiles is
+// empty after 65 us, the launch ends after 210 us with one or two lanes marching in the last warps). The reference
+// has no answer to that (one thread per ray, src/traverse.cu:28-38). Here the idle lanes of the warp take over:
+//
+//   * what is left of the ray, [t where it stands, far side of the grid or the hit in hand], is cut into up to 32
+//     segments, one per lane. Lane 0 continues from the exact state; lane g starts from the voxel recomputed at its
+//     cut point and enters that cell WITHOUT testing it -- which leaves it in a state (voxel, hit in hand) that the
+//     exact march may or may not pass through;
+//   * all lanes march in step. A lane records the first four states it passes as marks. The march is a pure
+//     function of the state (voxel, hit in hand): as soon as lane g stands in a state equal to a mark of lane g+1,
+//     with the hit it started with still unchanged on both sides, everything lane g+1 did from that mark on IS what
+//     lane g would do next, and lane g stops ("joined"). Cells overlap after expand_grid, so two marches of one ray
+//     can take a few cells to fall into step: over the 40 000 longest rays of that frame the join happens at mark 0
+//     in 85 %, within four marks in all but 0.005 % (CPU model of this procedure, oracle og_traverse_split);
+//   * a lane that finds no mark simply marches on to the end of the ray: slower, never different;
+//   * the result is read off the chain: lanes 0 .. c-1 joined, lane c ended (hit, or left the grid): hit of lane c,
+//     steps = what every lane of the chain contributed between its entry point and its join.
+//
+// Every float operation that decides anything is the march's own (visit_cell); where the cuts are placed changes
+// speed, not results. tests/: bit-identical ids, t and step counts against the reference with every ray split.
+// ---------------------------------------------------------------------------
 #ifdef HGB_TILE_TRACE
 // Diagnosis build only (tools/gpu_tile_variants.py): per warp [first tile started, last tile finished, tiles traced], ns
 __device__ long long g_tile_trace[3 * 8192];
+__device__ unsigned long long g_split_stats[8];   // calls, segments, loop iterations, chain length, prologue cells, ns in split_walk
 __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
-template <typename CellT, bool kPrimId, int kAhead>
+struct SplitParams {
+    int budget;          // steps a tile marches before the rays that are not done are parked (0: nothing is parked)
+    int voxels;          // finest voxels along the ray's dominant axis per segment
+    int max_segments;    // segments (lanes) a round of the split march uses
+    int min_segments;    // fewer segments than this: not worth it, the ray marches on alone
+};
+
+constexpr int kSplitMarks = 4;
+
+__device__ __forceinline__ unsigned long long pack_voxel(const RayState& r) {
+    // states inside the grid only (virtual dims <= 2^21, checked on the host)
+    return (unsigned long long)unsigned(r.vx) | ((unsigned long long)unsigned(r.vy) << 21) | ((unsigned long long)unsigned(r.vz) << 42);
+}
+
+struct SplitResult { float hit_t; int hit_id; int steps; };
+
+/// All 32 lanes, with the interrupted ray of one parked slot broadcast to all: finishes that ray; returns its final hit
+/// and the steps taken from here on. The ray is worked off in rounds: a round looks `max_segments` segments of
+/// `voxels` finest voxels ahead (most long rays end soon after they were parked; what lies beyond is not touched),
+/// the last segment marches a few cells and reports where it stands, and the next round starts from that state.
+template <typename CellT>
+__device__ __forceinline__ SplitResult split_walk(float ox, float oy, float oz, float tmin, float dx, float dy, float dz,
+                                                  float hit_t0, int hit_id0, int vx, int vy, int vz, float t0,
+                                                  const TraversalParams& P, const SplitParams& S,
+                                                  const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
+                                                  const int* __restrict__ ref_ids, const Tri* __restrict__ tris) {
+    using namespace dev;
+    constexpr unsigned kAll = 0xFFFFFFFFu;
+    constexpr int kLastCells = 4;          // cells the last segment of a round marches beyond its recorded ones
+    const int lane = threadIdx.x & 31;
+    RayState q;
+    q.ox = ox; q.oy = oy; q.oz = oz; q.tmin = tmin; q.dx = dx; q.dy = dy; q.dz = dz;
+    q.ix = safe_rcp(q.dx); q.iy = safe_rcp(q.dy); q.iz = safe_rcp(q.dz);
+    // plain float arithmetic below places the cuts; it decides nothing
+    const float far_t = fminf(sel_max((P.min_x - q.ox) * q.ix, (P.max_x - q.ox) * q.ix),
+                              fminf(sel_max((P.min_y - q.oy) * q.iy, (P.max_y - q.oy) * q.iy),
+                                    sel_max((P.min_z - q.oz) * q.iz, (P.max_z - q.oz) * q.iz)));
+    const float speed = fmaxf(fabsf(q.dx) * P.inv_x, fmaxf(fabsf(q.dy) * P.inv_y, fabsf(q.dz) * P.inv_z));   // finest voxels per unit t
+    const float segment_t = float(S.voxels) / speed;
+    int steps_total = 0;
+#ifdef HGB_TILE_TRACE
+    int iterations = 0, rounds = 0, segments = 0;
+    const long long entered = global_ns();
+#endif
+
+    while (true) {
+        // ---- one round, from the exact state (vx, vy, vz, t0, hit in hand)
+        const float reach = (fminf(far_t, hit_t0) - t0) * speed;
+        int count = 1;
+        if (reach > 0.0f && reach < 1e9f && segment_t > 0.0f) count = min(S.max_segments, int(reach / float(S.voxels)) + 1);
+        if (count < S.min_segments) count = 1;
+#ifdef HGB_TILE_TRACE
+        rounds++; segments += count;
+#endif
+        q.vx = vx; q.vy = vy; q.vz = vz;
+        q.hit_t = hit_t0; q.hit_id = hit_id0; q.steps = 0; q.tlast = t0;
+        if (count == 1) {
+            // nothing to share out: lane 0 marches to the end of the ray
+            if (lane == 0) walk<CellT, -1, false>(q, P, entries, cells, ref_ids, tris);
+            SplitResult res;
+            res.hit_t = __shfl_sync(kAll, q.hit_t, 0);
+            res.hit_id = __shfl_sync(kAll, q.hit_id, 0);
+            res.steps = steps_total + __shfl_sync(kAll, q.steps, 0);
+#ifdef HGB_TILE_TRACE
+            if (lane == 0) {
+                atomicAdd(g_split_stats + 0, 1ull); atomicAdd(g_split_stats + 1, (unsigned long long)segments);
+                atomicAdd(g_split_stats + 2, (unsigned long long)iterations); atomicAdd(g_split_stats + 3, (unsigned long long)rounds);
+                atomicAdd(g_split_stats + 5, (unsigned long long)(global_ns() - entered));
+            }
+#endif
+            return res;
+        }
+
+        // 0 = marching, 1 = ended (hit or left the grid: final), 2 = joined the next segment, 3 = interrupted (last segment)
+        int state = lane < count ? 0 : 1;
+        if (lane > 0 && lane < count) {
+            const float ts = t0 + segment_t * float(lane);
+            q.vx = min(P.dims_x - 1, max(0, trunc_to_int(mul(sub(fma(q.dx, ts, q.ox), P.min_x), P.inv_x))));
+            q.vy = min(P.dims_y - 1, max(0, trunc_to_int(mul(sub(fma(q.dy, ts, q.oy), P.min_y), P.inv_y))));
+            q.vz = min(P.dims_z - 1, max(0, trunc_to_int(mul(sub(fma(q.dz, ts, q.oz), P.min_z), P.inv_z))));
+            CellBox untested;
+            enter_cell<CellT, -1>(q, P, entries, cells, untested);
+            if (left_grid(q, P)) state = 1;              // a state the march can only reach by ending: nobody joins it
+        }
+
+        unsigned long long mark[kSplitMarks], next_mark[kSplitMarks];
+        int mark_steps[kSplitMarks], next_steps[kSplitMarks];
+        int marks = 0;
+#pragma unroll
+        for (int i = 0; i < kSplitMarks; i++) { mark[i] = ~0ull; mark_steps[i] = 0; }
+        auto clean = [&] { return q.hit_id == hit_id0 && q.hit_t == hit_t0; };
+        auto advance = [&] {
+            const float texit = visit_cell<CellT, -1>(q, P, entries, cells, ref_ids, tris);
+            q.tlast = texit;
+            if (q.hit_t <= texit || left_grid(q, P)) state = 1;
+        };
+        // the first cells of every segment, their states recorded (while the hit in hand is the one the round started with)
+#pragma unroll
+        for (int i = 0; i < kSplitMarks; i++) {
+            if (state == 0) {
+                if (marks == i && clean()) { mark[i] = pack_voxel(q); mark_steps[i] = q.steps; marks = i + 1; }
+                advance();
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kSplitMarks; i++) {
+            next_mark[i] = __shfl_down_sync(kAll, mark[i], 1);
+            next_steps[i] = __shfl_down_sync(kAll, mark_steps[i], 1);
+        }
+        int next_marks = __shfl_down_sync(kAll, marks, 1);
+        if (lane + 1 >= count) next_marks = 0;
+
+        int own_steps = 0;       // steps this lane contributes, up to where it joined
+        int join_skip = 0;       // steps the next lane had already taken at the mark this lane joined
+        // did one of the states just recorded already stand on a mark of the next segment?
+        if (state == 0) {
+#pragma unroll
+            for (int j = kSplitMarks - 1; j >= 0; j--)
+#pragma unroll
+                for (int k = 0; k < kSplitMarks; k++)
+                    if (j < marks && k < next_marks && mark[j] == next_mark[k]) { state = 2; own_steps = mark_steps[j]; join_skip = next_steps[k]; }
+        }
+
+        int last = 0;            // lane the chain ends in
+        int extra = 0;           // cells the last segment has marched beyond the recorded ones
+        while (true) {
+#ifdef HGB_TILE_TRACE
+            iterations++;
+#endif
+            const unsigned stopped = __ballot_sync(kAll, state == 1 || state == 3), joined = __ballot_sync(kAll, state == 2);
+            if (stopped) {
+                last = __ffs(stopped) - 1;
+                const unsigned before = (1u << last) - 1u;
+                if ((joined & before) == before) break;  // lanes 0 .. last-1 joined, lane `last` ended or stands: the chain is complete
+            }
+            if (state == 0) {
+                if (clean()) {
+                    const unsigned long long here = pack_voxel(q);
+#pragma unroll
+                    for (int k = 0; k < kSplitMarks; k++)
+                        if (k < next_marks && here == next_mark[k]) { state = 2; own_steps = q.steps; join_skip = next_steps[k]; }
+                }
+                if (state == 0) {
+                    if (lane == count - 1 && extra++ >= kLastCells) state = 3;
+                    else advance();
+                }
+            }
+        }
+
+        if (state == 1 || state == 3) own_steps = q.steps;
+        const int skip = __shfl_up_sync(kAll, join_skip, 1);
+        int total = lane <= last ? own_steps - (lane > 0 ? skip : 0) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(kAll, total, d);
+        steps_total += total;
+        hit_t0 = __shfl_sync(kAll, q.hit_t, last);
+        hit_id0 = __shfl_sync(kAll, q.hit_id, last);
+        if (__shfl_sync(kAll, state, last) == 1) break;
+        // the chain's last lane stands in the ray's true state: the next round starts there
+        vx = __shfl_sync(kAll, q.vx, last); vy = __shfl_sync(kAll, q.vy, last); vz = __shfl_sync(kAll, q.vz, last);
+        t0 = __shfl_sync(kAll, q.tlast, last);
+    }
+#ifdef HGB_TILE_TRACE
+    if (lane == 0) {
+        atomicAdd(g_split_stats + 0, 1ull); atomicAdd(g_split_stats + 1, (unsigned long long)segments);
+        atomicAdd(g_split_stats + 2, (unsigned long long)iterations); atomicAdd(g_split_stats + 3, (unsigned long long)rounds);
+        atomicAdd(g_split_stats + 5, (unsigned long long)(global_ns() - entered));
+    }
+#endif
+    SplitResult res;
+    res.hit_t = hit_t0;
+    res.hit_id = hit_id0;
+    res.steps = steps_total;
+    return res;
+}
+
+/// Rays parked by the tile phase of a launch (64 bytes each), served by the warps that have run out of tiles.
+/// `ready` carries the launch's epoch, so the array never has to be cleared.
+struct ParkedRay {
+    float ox, oy, oz, tmin;
+    float dx, dy, dz, hit_t;
+    int   vx, vy, vz, hit_id;
+    float tlast; int steps; int ray; unsigned ready;
+};
+static_assert(sizeof(ParkedRay) == 64, "four 16-byte words");
+
+struct StragglerQueue {
+    ParkedRay* slots;
+    unsigned capacity;           // 0: nothing is parked (every tile marches to its end)
+    unsigned* counters;          // [0] parked so far, [1] taken so far, [2] warps that have left the tile phase (zeroed by the host)
+    unsigned epoch;
+};
+
+__device__ __forceinline__ unsigned load_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+
+template <typename CellT, bool kPrimId>
 __global__ void __launch_bounds__(kTileBlock, kTileBlocksPerSm)
 traverse_tiles(const __grid_constant__ TraversalParams P,
                const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
                const int* __restrict__ layout, int host_width, unsigned* __restrict__ next_tile, unsigned ticket_base,
-               int* __restrict__ feedback, const __grid_constant__ ScenePrefetch scene) {
-    // kStage: while a tile is traced, the rays of the warp's next tile travel into shared memory (cp.async) and
-    // the fetch of the tile index after that is in flight: neither the atomic's round trip nor the HBM (or, for
-    // host-resident ray buffers, PCIe) latency of the ray loads sits between two tiles. Reserving a tile ahead
-    // lengthens the tail of the launch (an idle warp cannot take a tile another warp holds), so the last two
-    // rounds of tiles are fetched on demand as before.
-    constexpr bool kStage = kAhead == 2;
-    __shared__ float4 staged[kStage ? 2 * kTileBlock : 1];
+               int* __restrict__ feedback, const __grid_constant__ SplitParams S, const __grid_constant__ StragglerQueue Q) {
+    constexpr unsigned kAll = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     // feedback (device memory, may be null): [0] += warps whose rays did not share a direction octant, [1] += 1
     // per launch. A buffer of camera rays has a few such warps along the image axes; a buffer whose warps are
     // mostly mixed is not what this kernel is for: the host copies the words back now and then and moves such a
     // buffer to the incoherent kernel.
     if (feedback && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(feedback + 1, 1);
-    warm_l2(scene);
     const int width = layout ? __ldg(layout) : host_width;
     const int num_tiles = (num_rays + 31) >> 5;
     const int first_dynamic = gridDim.x * (kTileBlock / 32);
-    const int ahead_limit = num_tiles - 2 * first_dynamic;     // tiles below this index are traced with a successor in hand
-    int tile = blockIdx.x * (kTileBlock / 32) + (threadIdx.x >> 5);
-    int next = -1;                                             // kStage: tile held in reserve (-1: none)
-    bool have_staged = false;
 #ifdef HGB_TILE_TRACE
     const int trace_slot = blockIdx.x * (kTileBlock / 32) + (threadIdx.x >> 5);
     int traced_tiles = 0;
     if (lane == 0 && trace_slot < 8192) g_tile_trace[3 * trace_slot] = global_ns();
 #endif
+    // ---- tile phase: a tile marches for a budget of steps; rays that are not done by then are parked, so that no
+    // tile (and with it no launch) lasts as long as its longest ray
+    const int limit = Q.capacity ? S.budget : 0x7FFFFFFF;
+    int tile = blockIdx.x * (kTileBlock / 32) + (threadIdx.x >> 5);
     while (tile < num_tiles) {
         RayState r;
         bool ok = false;
-        {
-            int id = tile * 32 + lane;
-            if (id < num_rays) {
-                if (kStage && have_staged) {
-                    stage_wait();
-                    ok = init_ray(r, P, staged[2 * threadIdx.x], staged[2 * threadIdx.x + 1]);
-                } else {
-                    if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
-                    ok = start_ray(r, P, rays, id);
-                }
-            }
+        int id = tile * 32 + lane;
+        if (id < num_rays) {
+            if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
+            ok = start_ray(r, P, rays, id);
+        } else {
+            id = -1;
         }
-        have_staged = false;
-        if (kAhead && tile < ahead_limit) {
-            next = fetch_tile(next_tile, ticket_base, first_dynamic, lane);
-            int nid = next * 32 + lane;
-            if (next < num_tiles && nid < num_rays) {
-                if (width > 0) nid = tiled_ray_index_nodiv(next, lane, width);
-                if (kStage) {
-                    stage16(&staged[2 * threadIdx.x], reinterpret_cast<const float4*>(rays + nid));
-                    stage16(&staged[2 * threadIdx.x + 1], reinterpret_cast<const float4*>(rays + nid) + 1);
-                    have_staged = true;
-                } else {
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(rays + nid));
-                }
-            }
-        }
-        const bool uniform = walk_warp(ok, r, P, entries, cells, ref_ids, tris);
+        const bool uniform = walk_warp<CellT, true>(ok, r, P, entries, cells, ref_ids, tris, limit);
         if (!uniform && feedback && lane == 0) atomicAdd(feedback, 1);
-        {   // the ray's place in the buffer again (cheaper than keeping it in a register across the march)
-            int id = tile * 32 + lane;
-            if (id < num_rays) {
-                if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
-                finish_ray<kPrimId>(r, hits, id);
+        const unsigned rest = __ballot_sync(kAll, ok);
+        if (rest) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(Q.counters, unsigned(__popc(rest)));
+            base = __shfl_sync(kAll, base, 0);
+            if (ok) {
+                const unsigned slot = base + __popc(rest & ((1u << lane) - 1u));
+                if (slot < Q.capacity) {
+                    ParkedRay* dst = Q.slots + slot;
+                    float4* w = reinterpret_cast<float4*>(dst);
+                    w[0] = make_float4(r.ox, r.oy, r.oz, r.tmin);
+                    w[1] = make_float4(r.dx, r.dy, r.dz, r.hit_t);
+                    reinterpret_cast<int4*>(w)[2] = make_int4(r.vx, r.vy, r.vz, r.hit_id);
+                    dst->tlast = r.tlast; dst->steps = r.steps; dst->ray = id;
+                    __threadfence();
+                    *reinterpret_cast<volatile unsigned*>(&dst->ready) = Q.epoch;
+                    id = -1;                                   // whoever takes the slot writes the hit
+                } else {
+                    walk<CellT, -1, false>(r, P, entries, cells, ref_ids, tris);       // queue full: finish here
+                }
             }
         }
+        if (id >= 0) finish_ray<kPrimId>(r, hits, id);
         __syncwarp();
 #ifdef HGB_TILE_TRACE
         traced_tiles++;
         if (lane == 0 && trace_slot < 8192) { g_tile_trace[3 * trace_slot + 1] = global_ns(); g_tile_trace[3 * trace_slot + 2] = traced_tiles; }
 #endif
-        if (kAhead && next >= 0) { tile = next; next = -1; }
-        else tile = fetch_tile(next_tile, ticket_base, first_dynamic, lane);
+        tile = fetch_tile(next_tile, ticket_base, first_dynamic, lane);
+    }
+    if (!Q.capacity) return;
+
+    // ---- service phase: this warp has run out of tiles; it takes parked rays one at a time and finishes each with all
+    // its lanes (split_walk) until every warp has left the tile phase and every parked ray has been taken
+    __threadfence();
+    if (lane == 0) atomicAdd(Q.counters + 2, 1u);
+    const unsigned warps = gridDim.x * (kTileBlock / 32);
+    while (true) {
+        unsigned take = 0;
+        if (lane == 0) take = atomicAdd(Q.counters + 1, 1u);
+        take = __shfl_sync(kAll, take, 0);
+        if (take >= Q.capacity) break;
+        const ParkedRay* src = Q.slots + take;
+        bool have = false;
+        while (true) {
+            if (load_volatile(&src->ready) == Q.epoch) { have = true; break; }
+            if (load_volatile(Q.counters + 2) == warps) {
+                // nobody parks any more: the slot is either filled (and visible) or will never be
+                __threadfence();
+                have = take < min(load_volatile(Q.counters), Q.capacity);
+                break;
+            }
+            __nanosleep(256);
+        }
+        if (!have) break;
+        __threadfence();
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(src) + 0);
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(src) + 1);
+        const int4 c = __ldcg(reinterpret_cast<const int4*>(src) + 2);
+        const int4 d = __ldcg(reinterpret_cast<const int4*>(src) + 3);
+        const SplitResult res = split_walk<CellT>(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.w, c.x, c.y, c.z, __int_as_float(d.x),
+                                                  P, S, entries, cells, ref_ids, tris);
+        if (lane == 0)
+            dev::stg4_stream(hits + d.z, make_float4(__int_as_float(kPrimId ? res.hit_id : d.y + res.steps), res.hit_t, 0.0f, 0.0f));
     }
 }
 
@@ -778,6 +1011,9 @@ struct DeviceState {
     int feedback_mixed = 0, feedback_launches = 0;   // counter values when the current buffer was armed
     bool feedback_armed = false;
     int num_sms = 0;
+    ParkedRay* parked = nullptr;     // straggler queue of tile launches on the default stream
+    unsigned parked_capacity = 0, parked_epoch = 0;
+    unsigned* parked_counters = nullptr;
     // host-buffer frames (traverse_grid_host): one upload stream, one download stream, two traversal streams
     static constexpr int kStreams = 4, kMaxChunks = 64;
     cudaStream_t streams[kStreams] = {};            // 0 = upload, 1 = download, 2 and 3 = traversal
@@ -808,6 +1044,7 @@ DeviceState& device_state() {
         st.stream_tiles[1].word = reinterpret_cast<unsigned*>(st.words + 40);
         st.layout = st.words + 48;
         st.feedback_dev = st.words + 56;
+        st.parked_counters = reinterpret_cast<unsigned*>(st.words + 60);
         HGB_CUDA(cudaHostAlloc(&st.layout_host, 4 * sizeof(int), cudaHostAllocMapped));
         st.layout_host[0] = st.layout_host[1] = st.layout_host[2] = st.layout_host[3] = 0;
         st.feedback_host = st.layout_host + 2;
@@ -842,8 +1079,8 @@ std::atomic<int> g_host_frame_chunk{384 * 1024};
 std::atomic<int> g_host_frame_mode{0};
 // Host-buffer frames: > 0 = every chunk is this percentage of the rays still to go, 0 = chunks of equal size
 std::atomic<int> g_host_frame_fraction{0};
-// traverse_tiles: stage the next tile's rays through shared memory while the current tile is traced
-std::atomic<int> g_tile_stage{0};
+// traverse_tiles: parking and split march of stragglers (SplitParams); budget 0 = off
+std::atomic<int> g_split_budget{64}, g_split_voxels{64}, g_split_max_segments{8}, g_split_min_segments{2};
 // rasters smaller than this many rays are traced one thread per ray (re-tiled): a small launch does not fill the resident warps
 std::atomic<int> g_tile_min_rays{512 << 10};
 
@@ -857,30 +1094,25 @@ int traverse_variant() {
     return v;
 }
 
-// Triangle arrays this library has been shown with their length (build_grid / expand_grid receive it, traverse_grid
-// does not): lets a launch request the triangles into L2 along with the grid.
-std::mutex g_tri_lock;
-std::unordered_map<const void*, int> g_tri_counts;
-
-// L2 warm-up at the start of a tile launch: scenes up to this many bytes (0 = never)
-std::atomic<int> g_scene_prefetch_mb{64};
-
-ScenePrefetch scene_prefetch(const Grid& grid, const void* cells, size_t cell_bytes, const Tri* tris) {
-    ScenePrefetch S = {};
-    int num_tris = 0;
-    {
-        std::lock_guard<std::mutex> guard(g_tri_lock);
-        auto it = g_tri_counts.find(tris);
-        if (it != g_tri_counts.end()) num_tris = it->second;
+/// The straggler queue of a launch over `num_rays` rays on the default stream (null capacity: nothing is parked)
+StragglerQueue straggler_queue(DeviceState& st, const TraversalParams& P, int num_rays, cudaStream_t stream) {
+    StragglerQueue Q = {};
+    if (g_split_budget.load() <= 0 || max(P.dims_x, max(P.dims_y, P.dims_z)) > (1 << 21)) return Q;     // pack_voxel
+    const unsigned want = unsigned(std::max(num_rays / 4, 1 << 16));
+    if (want > st.parked_capacity) {
+        if (st.parked) HGB_CUDA(cudaFree(st.parked));
+        HGB_CUDA(cudaMalloc(&st.parked, sizeof(ParkedRay) * size_t(want)));
+        HGB_CUDA(cudaMemsetAsync(st.parked, 0, sizeof(ParkedRay) * size_t(want), stream));
+        st.parked_capacity = want;
+        st.parked_epoch = 0;
     }
-    const size_t bytes[4] = {size_t(grid.num_entries) * 4, size_t(grid.num_cells) * cell_bytes, size_t(grid.num_refs) * 4, size_t(num_tris) * sizeof(Tri)};
-    const void* base[4] = {grid.entries, cells, grid.ref_ids, tris};
-    if (bytes[0] + bytes[1] + bytes[2] + bytes[3] > size_t(g_scene_prefetch_mb.load()) << 20) return S;
-    for (int a = 0; a < 4; a++) {
-        S.base[a] = static_cast<const char*>(base[a]);
-        S.lines[a] = int((bytes[a] + 127) / 128);
+    if (++st.parked_epoch == 0) {       // wrapped: the flags of 2^32 launches ago must not look fresh
+        HGB_CUDA(cudaMemsetAsync(st.parked, 0, sizeof(ParkedRay) * size_t(st.parked_capacity), stream));
+        st.parked_epoch = 1;
     }
-    return S;
+    HGB_CUDA(cudaMemsetAsync(st.parked_counters, 0, 4 * sizeof(unsigned), stream));
+    Q.slots = st.parked; Q.capacity = st.parked_capacity; Q.counters = st.parked_counters; Q.epoch = st.parked_epoch;
+    return Q;
 }
 
 /// Enqueues one traversal launch on `stream`: 1 = persistent voting warps (needs `vote_counter`), 4 = resident
@@ -889,22 +1121,15 @@ ScenePrefetch scene_prefetch(const Grid& grid, const void* cells, size_t cell_by
 template <typename CellT, bool kPrimId>
 void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays,
              int variant, const int* layout, int host_width, int* vote_counter, Ticket& ticket, int num_sms, cudaStream_t stream,
-             int* feedback = nullptr) {
+             int* feedback = nullptr, DeviceState* park_in = nullptr) {
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
     const TraversalParams P = params_of(grid);
     if (variant == 4) {
         const int blocks = min(num_sms * kTileBlocksPerSm, round_div(num_rays, kTileBlock));
-        const int ahead = g_tile_stage.load();
-        const ScenePrefetch scene = scene_prefetch(grid, cells, sizeof(CellT), tris);
-        if (ahead == 2)
-            traverse_tiles<CellT, kPrimId, 2><<<blocks, kTileBlock, 0, stream>>>(
-                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback, scene);
-        else if (ahead == 1)
-            traverse_tiles<CellT, kPrimId, 1><<<blocks, kTileBlock, 0, stream>>>(
-                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback, scene);
-        else
-            traverse_tiles<CellT, kPrimId, 0><<<blocks, kTileBlock, 0, stream>>>(
-                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback, scene);
+        traverse_tiles<CellT, kPrimId><<<blocks, kTileBlock, 0, stream>>>(
+            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback,
+            SplitParams{g_split_budget.load(), g_split_voxels.load(), g_split_max_segments.load(), g_split_min_segments.load()},
+            park_in ? straggler_queue(*park_in, P, num_rays, stream) : StragglerQueue{});
         ticket.base += unsigned((num_rays + 31) >> 5);      // one fetch per traced tile (fetch_tile)
         count_launch();
     } else if (variant == 1) {
@@ -982,7 +1207,7 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
     // 5 (experiment): the voting kernel handed rays in tile order
     const bool tiled = variant == 2 || variant == 4 || variant == 5;
     enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant == 5 ? 1 : variant, tiled ? st.layout : nullptr, 0,
-                            st.vote_counter, st.tiles, st.num_sms, 0, feedback);
+                            st.vote_counter, st.tiles, st.num_sms, 0, feedback, &st);
     if (feedback) {
         // copied back after launches 1, 2, 4 and then every 8th: one 8-byte copy in eight launches
         const int tick = ++st.feedback_tick;
@@ -1165,12 +1390,6 @@ void dispatch(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int
 
 } // namespace
 
-void note_triangle_array(const Tri* tris, int num_tris) {
-    std::lock_guard<std::mutex> guard(g_tri_lock);
-    if (g_tri_counts.size() > 4096) g_tri_counts.clear();       // addresses are reused; the map is a hint, not a registry
-    g_tri_counts[tris] = num_tris;
-}
-
 void setup_traversal(const Grid& grid) {
     // Nothing to capture: the constants the reference stores in __constant__ memory here (src/traverse.cu:97-108)
     // are derived from the grid at every launch (params_of). The call creates the per-device launch state, so
@@ -1241,8 +1460,10 @@ bool set_traversal_option(const char* key, int value) {
     if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk.store(value > 0 ? value : 384 * 1024); return true; }
     if (!std::strcmp(key, "host_frame_mode")) { g_host_frame_mode.store(value < 0 || value > 3 ? 0 : value); return true; }
     if (!std::strcmp(key, "host_frame_fraction")) { g_host_frame_fraction.store(value < 0 || value > 90 ? 0 : value); return true; }
-    if (!std::strcmp(key, "tile_stage")) { g_tile_stage.store(value < 0 || value > 2 ? 0 : value); return true; }
-    if (!std::strcmp(key, "scene_prefetch_mb")) { g_scene_prefetch_mb.store(value < 0 ? 64 : value); return true; }
+    if (!std::strcmp(key, "split_budget")) { g_split_budget.store(value >= 0 ? value : 64); return true; }
+    if (!std::strcmp(key, "split_voxels")) { g_split_voxels.store(value > 0 ? value : 32); return true; }
+    if (!std::strcmp(key, "split_max_segments")) { g_split_max_segments.store(value > 0 ? min(value, 32) : 8); return true; }
+    if (!std::strcmp(key, "split_min_segments")) { g_split_min_segments.store(value > 0 ? value : 2); return true; }
     if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (512 << 10)); return true; }
     return false;
 }
@@ -1271,5 +1492,10 @@ void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays,
 #ifdef HGB_TILE_TRACE
 extern "C" __attribute__((visibility("default"))) int hgb_debug_tile_trace(long long* out) {
     return cudaMemcpyFromSymbol(out, hagrid::g_tile_trace, sizeof(long long) * 3 * 8192) == cudaSuccess ? 0 : -1;
+}
+extern "C" __attribute__((visibility("default"))) int hgb_debug_split_stats(unsigned long long* out, int reset) {
+    if (cudaMemcpyFromSymbol(out, hagrid::g_split_stats, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+    if (reset) { unsigned long long zero[8] = {}; cudaMemcpyToSymbol(hagrid::g_split_stats, zero, sizeof(zero)); }
+    return 0;
 }
 #endif

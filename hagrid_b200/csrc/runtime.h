@@ -21,11 +21,6 @@ inline void check_cuda(cudaError_t err, const char* what, const char* file, int 
 extern std::atomic<unsigned long long> g_kernel_launches;
 inline void count_launch(int n = 1) { g_kernel_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
-struct Tri;
-/// Tells the traversal how long a device triangle array is (build_grid and the C ABI know, traverse_grid's
-/// signature does not say): used to request the triangles into L2 at the start of a launch.
-void note_triangle_array(const Tri* tris, int num_tris);
-
 } // namespace hagrid
 
 #define HGB_CUDA(call) ::hagrid::check_cuda((call), #call, __FILE__, __LINE__)

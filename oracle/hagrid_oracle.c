@@ -1087,13 +1087,14 @@ void og_traverse_split(const og_grid* g, const og_tri* tris, const og_ray* rays,
                     walked[s] = q->cells;
                 }
                 /* the chain: from segment 0, enter segment s+1 at mark join_at[s]; what s+1 did before that mark is dropped */
-                int longest = 0, s = 0, skip_steps = 0, skip_cells = 0, entered = 0;
+                int longest = 0, s = 0, skip_steps = 0, skip_cells = 0, entered = 0, deepest = 0;
                 for (;; s++) {
                     if (!state[s] && join_at[s] >= 0) {
                         w.steps += seg[s].steps - skip_steps; w.cells += seg[s].cells - skip_cells;
                         const og_mark* m = marks + (size_t)(s + 1) * kHist + join_at[s];
                         /* segment s+1 must still have been running at that mark: true by construction (marks are states it left from) */
                         skip_steps = m->steps; skip_cells = m->cells; entered = join_at[s];
+                        if (entered > deepest) deepest = entered;
                         /* if s+1 itself joined s+2 before the mark we entered at, the rest of the chain is unusable: cannot happen,
                          * marks end where the segment ended */
                         continue;
@@ -1107,7 +1108,7 @@ void og_traverse_split(const og_grid* g, const og_tri* tris, const og_ray* rays,
                 for (int k = 0; k < count; k++)
                     if (walked[k] > longest) longest = walked[k];
                 critical += longest;
-                started = count;
+                started = count | (deepest << 8);
             }
             serial_cells = w.cells;
         }

@@ -72,9 +72,7 @@ def compare_buffer(tag, sr, sm, rays, settings, iters=30):
     return want
 
 
-SETTINGS = {"base": {"tile_stage": 0, "scene_prefetch_mb": 0}, "warm": {"tile_stage": 0, "scene_prefetch_mb": 64},
-            "ahead": {"tile_stage": 1, "scene_prefetch_mb": 0}, "ahead_warm": {"tile_stage": 1, "scene_prefetch_mb": 64},
-            "staged_warm": {"tile_stage": 2, "scene_prefetch_mb": 64}}
+SETTINGS = {"plain": {"tile_pipeline": 0}, "pipelined": {"tile_pipeline": 1}}
 
 if "c2" in what or "e2e" in what or "shards" in what:
     tris = scenes.sponza262k()
@@ -90,8 +88,8 @@ if "c2" in what or "e2e" in what or "shards" in what:
             idx = sharding.interleaved_bands(primary.shape[0], 0, world, sharding.raster_granule(W))
             part = np.ascontiguousarray(primary[idx])
             compare_buffer(f"c2_shard_1of{world}", sr, sm, part,
-                           {"per_thread": {"tile_stage": 0, "tile_min_rays": 1 << 30}, "tiles": {"tile_stage": 0, "tile_min_rays": 0, "scene_prefetch_mb": 0},
-                            "tiles_warm": {"tile_stage": 0, "tile_min_rays": 0, "scene_prefetch_mb": 64}}, 30)
+                           {"per_thread": {"tile_min_rays": 1 << 30}, "tiles": {"tile_pipeline": 0, "tile_min_rays": 0},
+                            "tiles_pipelined": {"tile_pipeline": 1, "tile_min_rays": 0}}, 30)
         mine.set_option("tile_min_rays", -1)
     if "e2e" in what:
         n = primary.shape[0]
@@ -103,8 +101,8 @@ if "c2" in what or "e2e" in what or "shards" in what:
         res["reference"] = r
         for mode in (0, 1):
             for stage in (0,):
-                for chunk in (128, 160, 192, 224, 256, 288, 320):
-                    mine.set_option("host_frame_mode", mode); mine.set_option("tile_stage", stage); mine.set_option("host_frame_chunk_rays", chunk * 1024)
+                for chunk in (224, 256, 288):
+                    mine.set_option("host_frame_mode", mode); mine.set_option("host_frame_chunk_rays", chunk * 1024)
                     h_hits.zero_()
                     t = timed(lambda: mine.check(mine.dll.hgb_traverse_grid_host(sm._h, h_rays.data_ptr(), h_hits.data_ptr(), n, HIT_PRIM_ID), "f"), 20, 3)
                     t["identical"] = bool(np.array_equal(h_hits.numpy().view(np.int32)[:, 0], want["id"]) and
@@ -122,7 +120,7 @@ if "c5" in what:
     primary = scenes.default_view(tris)
     first = compare_buffer("c5_primary", sr, sm, primary, SETTINGS, 30)
     bounce = scenes.bounce_rays(tris, primary, first["id"], first["t"].view(np.float32))
-    compare_buffer("c5_bounce", sr, sm, bounce, {"default": {"tile_stage": 0}}, 10)
+    compare_buffer("c5_bounce", sr, sm, bounce, {"default": {}}, 10)
     sr.close(); sm.close()
 
 Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
