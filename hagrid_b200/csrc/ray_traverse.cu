@@ -33,7 +33,7 @@
 
 // Build-time tuning knobs of the tile kernel (tools/gpu_tile_variants.py builds the alternatives)
 #ifndef HGB_TILE_BLOCKS
-#define HGB_TILE_BLOCKS 10
+#define HGB_TILE_BLOCKS 12
 #endif
 #ifndef HGB_REF_UNROLL
 #define HGB_REF_UNROLL 1                 // 0: ptxas decides (it unrolls four-fold)
@@ -91,7 +91,6 @@ struct RayState {
     int   hit_id;
     int   steps;
     int   vx, vy, vz;                   // current voxel
-    float tlast;                        // where the march stood when it was interrupted (walk with a step budget)
 };
 
 /// Ray/triangle test, expression shapes as in the reference SASS:
@@ -331,17 +330,15 @@ __device__ __forceinline__ bool left_grid(const RayState& r, const TraversalPara
     return (unsigned(r.vx) >= unsigned(P.dims_x)) | (unsigned(r.vy) >= unsigned(P.dims_y)) | (unsigned(r.vz) >= unsigned(P.dims_z));
 }
 
-/// The march of one ray through the grid after init_ray (src/traverse.cu:56-90). kBudget: the march is interrupted
-/// (returns false, r.tlast = where it stands) once the ray has taken `limit` steps; it continues with the next call.
-template <typename CellT, int kOct = -1, bool kBudget = false>
-__device__ __forceinline__ bool walk(RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
+/// The march of one ray through the grid after init_ray (src/traverse.cu:56-90)
+template <typename CellT, int kOct = -1>
+__device__ __forceinline__ void walk(RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
                                      const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
-                                     const Tri* __restrict__ tris, int limit = 0) {
+                                     const Tri* __restrict__ tris) {
     while (true) {
         const float texit = visit_cell<CellT, kOct>(r, P, entries, cells, ref_ids, tris);
-        if (r.hit_t <= texit) return true;
-        if (left_grid(r, P)) return true;
-        if (kBudget && r.steps >= limit) { r.tlast = texit; return false; }
+        if (r.hit_t <= texit) break;
+        if (left_grid(r, P)) break;
     }
 }
 
@@ -382,12 +379,11 @@ __device__ __forceinline__ int octant_of(const RayState& r) {
 
 /// March of the lanes with `ok` set. Called by all 32 lanes of a converged warp: when every marching lane has
 /// the same direction octant — the rule for an 8x4 tile of camera rays — the warp takes the loop specialised
-/// for it, otherwise the generic one. Same cells, same triangles, same order either way. kBudget: lanes whose
-/// ray is not finished after `limit` steps come back with `ok` still set.
-template <typename CellT, bool kBudget = false>
-__device__ __forceinline__ bool walk_warp(bool& ok, RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
+/// for it, otherwise the generic one. Same cells, same triangles, same order either way.
+template <typename CellT>
+__device__ __forceinline__ bool walk_warp(bool ok, RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
                                           const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
-                                          const Tri* __restrict__ tris, int limit = 0) {
+                                          const Tri* __restrict__ tris) {
     constexpr unsigned kAll = 0xFFFFFFFFu;
     const unsigned marching = __ballot_sync(kAll, ok);
     if (marching == 0) return true;
@@ -395,22 +391,20 @@ __device__ __forceinline__ bool walk_warp(bool& ok, RayState& r, const Traversal
     const int first = __shfl_sync(kAll, oct, __ffs(marching) - 1);
     const bool uniform = __all_sync(kAll, !ok || oct == first);
     if (!ok) return uniform;
-    bool done;
     if (uniform) {
         switch (first) {
-            case 0: done = walk<CellT, 0, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 1: done = walk<CellT, 1, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 2: done = walk<CellT, 2, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 3: done = walk<CellT, 3, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 4: done = walk<CellT, 4, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 5: done = walk<CellT, 5, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 6: done = walk<CellT, 6, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            default: done = walk<CellT, 7, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
+            case 0: walk<CellT, 0>(r, P, entries, cells, ref_ids, tris); break;
+            case 1: walk<CellT, 1>(r, P, entries, cells, ref_ids, tris); break;
+            case 2: walk<CellT, 2>(r, P, entries, cells, ref_ids, tris); break;
+            case 3: walk<CellT, 3>(r, P, entries, cells, ref_ids, tris); break;
+            case 4: walk<CellT, 4>(r, P, entries, cells, ref_ids, tris); break;
+            case 5: walk<CellT, 5>(r, P, entries, cells, ref_ids, tris); break;
+            case 6: walk<CellT, 6>(r, P, entries, cells, ref_ids, tris); break;
+            default: walk<CellT, 7>(r, P, entries, cells, ref_ids, tris); break;
         }
     } else {
-        done = walk<CellT, -1, kBudget>(r, P, entries, cells, ref_ids, tris, limit);
+        walk<CellT, -1>(r, P, entries, cells, ref_ids, tris);
     }
-    ok = !done;
     return uniform;
 }
 
@@ -421,7 +415,7 @@ __device__ __forceinline__ bool walk_warp(bool& ok, RayState& r, const Traversal
 // warp picks specialised for its direction octant when all its rays share one (walk_warp).
 // ---------------------------------------------------------------------------
 constexpr int kTileBlock = 128;
-constexpr int kTileBlocksPerSm = HGB_TILE_BLOCKS;     // 10: <= 51 registers, 40 resident warps per SM, measured best of 8 / 10 / 12
+constexpr int kTileBlocksPerSm = HGB_TILE_BLOCKS;     // 12 blocks = 48 warps per SM at 40 registers (reference loop not unrolled): measured best, profiles/r02_traverse_experiments.md
 
 /// Tile hand-out without a reset: the counter only ever grows, the host passes the value it has at the start
 /// of the launch (`base`). Every traced tile is followed by exactly one fetch, so a launch over T tiles advances
@@ -434,231 +428,11 @@ __device__ __forceinline__ int fetch_tile(unsigned* __restrict__ next_tile, unsi
 }
 
 
-// ---------------------------------------------------------------------------
-// Split march of a straggler. A tile is done when its longest ray is done, a launch when its longest tile is: on the
-// 7.8 M-triangle scene the mean ray takes 8 steps, the longest 347 (155 cells), and that one ray -- a chain of
-// dependent L2 round trips, cell after cell -- lasts as long as the rest of the frame together (the queue of tiles is
-// empty after 65 us, the launch ends after 210 us with one or two lanes marching in the last warps). The reference
-// has no answer to that (one thread per ray, src/traverse.cu:28-38). Here the idle lanes of the warp take over:
-//
-//   * what is left of the ray, [t where it stands, far side of the grid or the hit in hand], is cut into up to 32
-//     segments, one per lane. Lane 0 continues from the exact state; lane g starts from the voxel recomputed at its
-//     cut point and enters that cell WITHOUT testing it -- which leaves it in a state (voxel, hit in hand) that the
-//     exact march may or may not pass through;
-//   * all lanes march in step. A lane records the first four states it passes as marks. The march is a pure
-//     function of the state (voxel, hit in hand): as soon as lane g stands in a state equal to a mark of lane g+1,
-//     with the hit it started with still unchanged on both sides, everything lane g+1 did from that mark on IS what
-//     lane g would do next, and lane g stops ("joined"). Cells overlap after expand_grid, so two marches of one ray
-//     can take a few cells to fall into step: over the 40 000 longest rays of that frame the join happens at mark 0
-//     in 85 %, within four marks in all but 0.005 % (CPU model of this procedure, oracle og_traverse_split);
-//   * a lane that finds no mark simply marches on to the end of the ray: slower, never different;
-//   * the result is read off the chain: lanes 0 .. c-1 joined, lane c ended (hit, or left the grid): hit of lane c,
-//     steps = what every lane of the chain contributed between its entry point and its join.
-//
-// Every float operation that decides anything is the march's own (visit_cell); where the cuts are placed changes
-// speed, not results. tests/: bit-identical ids, t and step counts against the reference with every ray split.
-// ---------------------------------------------------------------------------
 #ifdef HGB_TILE_TRACE
 // Diagnosis build only (tools/gpu_tile_variants.py): per warp [first tile started, last tile finished, tiles traced], ns
 __device__ long long g_tile_trace[3 * 8192];
-__device__ unsigned long long g_split_stats[8];   // calls, segments, loop iterations, chain length, prologue cells, ns in split_walk
 __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
-
-struct SplitParams {
-    int budget;          // steps a tile marches before the rays that are not done are parked (0: nothing is parked)
-    int voxels;          // finest voxels along the ray's dominant axis per segment
-    int max_segments;    // segments (lanes) a round of the split march uses
-    int min_segments;    // fewer segments than this: not worth it, the ray marches on alone
-};
-
-constexpr int kSplitMarks = 4;
-
-__device__ __forceinline__ unsigned long long pack_voxel(const RayState& r) {
-    // states inside the grid only (virtual dims <= 2^21, checked on the host)
-    return (unsigned long long)unsigned(r.vx) | ((unsigned long long)unsigned(r.vy) << 21) | ((unsigned long long)unsigned(r.vz) << 42);
-}
-
-struct SplitResult { float hit_t; int hit_id; int steps; };
-
-/// All 32 lanes, with the interrupted ray of one parked slot broadcast to all: finishes that ray; returns its final hit
-/// and the steps taken from here on. The ray is worked off in rounds: a round looks `max_segments` segments of
-/// `voxels` finest voxels ahead (most long rays end soon after they were parked; what lies beyond is not touched),
-/// the last segment marches a few cells and reports where it stands, and the next round starts from that state.
-template <typename CellT>
-__device__ __forceinline__ SplitResult split_walk(float ox, float oy, float oz, float tmin, float dx, float dy, float dz,
-                                                  float hit_t0, int hit_id0, int vx, int vy, int vz, float t0,
-                                                  const TraversalParams& P, const SplitParams& S,
-                                                  const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
-                                                  const int* __restrict__ ref_ids, const Tri* __restrict__ tris) {
-    using namespace dev;
-    constexpr unsigned kAll = 0xFFFFFFFFu;
-    constexpr int kLastCells = 4;          // cells the last segment of a round marches beyond its recorded ones
-    const int lane = threadIdx.x & 31;
-    RayState q;
-    q.ox = ox; q.oy = oy; q.oz = oz; q.tmin = tmin; q.dx = dx; q.dy = dy; q.dz = dz;
-    q.ix = safe_rcp(q.dx); q.iy = safe_rcp(q.dy); q.iz = safe_rcp(q.dz);
-    // plain float arithmetic below places the cuts; it decides nothing
-    const float far_t = fminf(sel_max((P.min_x - q.ox) * q.ix, (P.max_x - q.ox) * q.ix),
-                              fminf(sel_max((P.min_y - q.oy) * q.iy, (P.max_y - q.oy) * q.iy),
-                                    sel_max((P.min_z - q.oz) * q.iz, (P.max_z - q.oz) * q.iz)));
-    const float speed = fmaxf(fabsf(q.dx) * P.inv_x, fmaxf(fabsf(q.dy) * P.inv_y, fabsf(q.dz) * P.inv_z));   // finest voxels per unit t
-    const float segment_t = float(S.voxels) / speed;
-    int steps_total = 0;
-#ifdef HGB_TILE_TRACE
-    int iterations = 0, rounds = 0, segments = 0;
-    const long long entered = global_ns();
-#endif
-
-    while (true) {
-        // ---- one round, from the exact state (vx, vy, vz, t0, hit in hand)
-        const float reach = (fminf(far_t, hit_t0) - t0) * speed;
-        int count = 1;
-        if (reach > 0.0f && reach < 1e9f && segment_t > 0.0f) count = min(S.max_segments, int(reach / float(S.voxels)) + 1);
-        if (count < S.min_segments) count = 1;
-#ifdef HGB_TILE_TRACE
-        rounds++; segments += count;
-#endif
-        q.vx = vx; q.vy = vy; q.vz = vz;
-        q.hit_t = hit_t0; q.hit_id = hit_id0; q.steps = 0; q.tlast = t0;
-        if (count == 1) {
-            // nothing to share out: lane 0 marches to the end of the ray
-            if (lane == 0) walk<CellT, -1, false>(q, P, entries, cells, ref_ids, tris);
-            SplitResult res;
-            res.hit_t = __shfl_sync(kAll, q.hit_t, 0);
-            res.hit_id = __shfl_sync(kAll, q.hit_id, 0);
-            res.steps = steps_total + __shfl_sync(kAll, q.steps, 0);
-#ifdef HGB_TILE_TRACE
-            if (lane == 0) {
-                atomicAdd(g_split_stats + 0, 1ull); atomicAdd(g_split_stats + 1, (unsigned long long)segments);
-                atomicAdd(g_split_stats + 2, (unsigned long long)iterations); atomicAdd(g_split_stats + 3, (unsigned long long)rounds);
-                atomicAdd(g_split_stats + 5, (unsigned long long)(global_ns() - entered));
-            }
-#endif
-            return res;
-        }
-
-        // 0 = marching, 1 = ended (hit or left the grid: final), 2 = joined the next segment, 3 = interrupted (last segment)
-        int state = lane < count ? 0 : 1;
-        if (lane > 0 && lane < count) {
-            const float ts = t0 + segment_t * float(lane);
-            q.vx = min(P.dims_x - 1, max(0, trunc_to_int(mul(sub(fma(q.dx, ts, q.ox), P.min_x), P.inv_x))));
-            q.vy = min(P.dims_y - 1, max(0, trunc_to_int(mul(sub(fma(q.dy, ts, q.oy), P.min_y), P.inv_y))));
-            q.vz = min(P.dims_z - 1, max(0, trunc_to_int(mul(sub(fma(q.dz, ts, q.oz), P.min_z), P.inv_z))));
-            CellBox untested;
-            enter_cell<CellT, -1>(q, P, entries, cells, untested);
-            if (left_grid(q, P)) state = 1;              // a state the march can only reach by ending: nobody joins it
-        }
-
-        unsigned long long mark[kSplitMarks], next_mark[kSplitMarks];
-        int mark_steps[kSplitMarks], next_steps[kSplitMarks];
-        int marks = 0;
-#pragma unroll
-        for (int i = 0; i < kSplitMarks; i++) { mark[i] = ~0ull; mark_steps[i] = 0; }
-        auto clean = [&] { return q.hit_id == hit_id0 && q.hit_t == hit_t0; };
-        auto advance = [&] {
-            const float texit = visit_cell<CellT, -1>(q, P, entries, cells, ref_ids, tris);
-            q.tlast = texit;
-            if (q.hit_t <= texit || left_grid(q, P)) state = 1;
-        };
-        // the first cells of every segment, their states recorded (while the hit in hand is the one the round started with)
-#pragma unroll
-        for (int i = 0; i < kSplitMarks; i++) {
-            if (state == 0) {
-                if (marks == i && clean()) { mark[i] = pack_voxel(q); mark_steps[i] = q.steps; marks = i + 1; }
-                advance();
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kSplitMarks; i++) {
-            next_mark[i] = __shfl_down_sync(kAll, mark[i], 1);
-            next_steps[i] = __shfl_down_sync(kAll, mark_steps[i], 1);
-        }
-        int next_marks = __shfl_down_sync(kAll, marks, 1);
-        if (lane + 1 >= count) next_marks = 0;
-
-        int own_steps = 0;       // steps this lane contributes, up to where it joined
-        int join_skip = 0;       // steps the next lane had already taken at the mark this lane joined
-        // did one of the states just recorded already stand on a mark of the next segment?
-        if (state == 0) {
-#pragma unroll
-            for (int j = kSplitMarks - 1; j >= 0; j--)
-#pragma unroll
-                for (int k = 0; k < kSplitMarks; k++)
-                    if (j < marks && k < next_marks && mark[j] == next_mark[k]) { state = 2; own_steps = mark_steps[j]; join_skip = next_steps[k]; }
-        }
-
-        int last = 0;            // lane the chain ends in
-        int extra = 0;           // cells the last segment has marched beyond the recorded ones
-        while (true) {
-#ifdef HGB_TILE_TRACE
-            iterations++;
-#endif
-            const unsigned stopped = __ballot_sync(kAll, state == 1 || state == 3), joined = __ballot_sync(kAll, state == 2);
-            if (stopped) {
-                last = __ffs(stopped) - 1;
-                const unsigned before = (1u << last) - 1u;
-                if ((joined & before) == before) break;  // lanes 0 .. last-1 joined, lane `last` ended or stands: the chain is complete
-            }
-            if (state == 0) {
-                if (clean()) {
-                    const unsigned long long here = pack_voxel(q);
-#pragma unroll
-                    for (int k = 0; k < kSplitMarks; k++)
-                        if (k < next_marks && here == next_mark[k]) { state = 2; own_steps = q.steps; join_skip = next_steps[k]; }
-                }
-                if (state == 0) {
-                    if (lane == count - 1 && extra++ >= kLastCells) state = 3;
-                    else advance();
-                }
-            }
-        }
-
-        if (state == 1 || state == 3) own_steps = q.steps;
-        const int skip = __shfl_up_sync(kAll, join_skip, 1);
-        int total = lane <= last ? own_steps - (lane > 0 ? skip : 0) : 0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(kAll, total, d);
-        steps_total += total;
-        hit_t0 = __shfl_sync(kAll, q.hit_t, last);
-        hit_id0 = __shfl_sync(kAll, q.hit_id, last);
-        if (__shfl_sync(kAll, state, last) == 1) break;
-        // the chain's last lane stands in the ray's true state: the next round starts there
-        vx = __shfl_sync(kAll, q.vx, last); vy = __shfl_sync(kAll, q.vy, last); vz = __shfl_sync(kAll, q.vz, last);
-        t0 = __shfl_sync(kAll, q.tlast, last);
-    }
-#ifdef HGB_TILE_TRACE
-    if (lane == 0) {
-        atomicAdd(g_split_stats + 0, 1ull); atomicAdd(g_split_stats + 1, (unsigned long long)segments);
-        atomicAdd(g_split_stats + 2, (unsigned long long)iterations); atomicAdd(g_split_stats + 3, (unsigned long long)rounds);
-        atomicAdd(g_split_stats + 5, (unsigned long long)(global_ns() - entered));
-    }
-#endif
-    SplitResult res;
-    res.hit_t = hit_t0;
-    res.hit_id = hit_id0;
-    res.steps = steps_total;
-    return res;
-}
-
-/// Rays parked by the tile phase of a launch (64 bytes each), served by the warps that have run out of tiles.
-/// `ready` carries the launch's epoch, so the array never has to be cleared.
-struct ParkedRay {
-    float ox, oy, oz, tmin;
-    float dx, dy, dz, hit_t;
-    int   vx, vy, vz, hit_id;
-    float tlast; int steps; int ray; unsigned ready;
-};
-static_assert(sizeof(ParkedRay) == 64, "four 16-byte words");
-
-struct StragglerQueue {
-    ParkedRay* slots;
-    unsigned capacity;           // 0: nothing is parked (every tile marches to its end)
-    unsigned* counters;          // [0] parked so far, [1] taken so far, [2] warps that have left the tile phase (zeroed by the host)
-    unsigned epoch;
-};
-
-__device__ __forceinline__ unsigned load_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
 
 template <typename CellT, bool kPrimId>
 __global__ void __launch_bounds__(kTileBlock, kTileBlocksPerSm)
@@ -667,8 +441,7 @@ traverse_tiles(const __grid_constant__ TraversalParams P,
                const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
                const int* __restrict__ layout, int host_width, unsigned* __restrict__ next_tile, unsigned ticket_base,
-               int* __restrict__ feedback, const __grid_constant__ SplitParams S, const __grid_constant__ StragglerQueue Q) {
-    constexpr unsigned kAll = 0xFFFFFFFFu;
+               int* __restrict__ feedback) {
     const int lane = threadIdx.x & 31;
     // feedback (device memory, may be null): [0] += warps whose rays did not share a direction octant, [1] += 1
     // per launch. A buffer of camera rays has a few such warps along the image axes; a buffer whose warps are
@@ -683,86 +456,32 @@ traverse_tiles(const __grid_constant__ TraversalParams P,
     int traced_tiles = 0;
     if (lane == 0 && trace_slot < 8192) g_tile_trace[3 * trace_slot] = global_ns();
 #endif
-    // ---- tile phase: a tile marches for a budget of steps; rays that are not done by then are parked, so that no
-    // tile (and with it no launch) lasts as long as its longest ray
-    const int limit = Q.capacity ? S.budget : 0x7FFFFFFF;
     int tile = blockIdx.x * (kTileBlock / 32) + (threadIdx.x >> 5);
     while (tile < num_tiles) {
         RayState r;
         bool ok = false;
-        int id = tile * 32 + lane;
-        if (id < num_rays) {
-            if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
-            ok = start_ray(r, P, rays, id);
-        } else {
-            id = -1;
-        }
-        const bool uniform = walk_warp<CellT, true>(ok, r, P, entries, cells, ref_ids, tris, limit);
-        if (!uniform && feedback && lane == 0) atomicAdd(feedback, 1);
-        const unsigned rest = __ballot_sync(kAll, ok);
-        if (rest) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(Q.counters, unsigned(__popc(rest)));
-            base = __shfl_sync(kAll, base, 0);
-            if (ok) {
-                const unsigned slot = base + __popc(rest & ((1u << lane) - 1u));
-                if (slot < Q.capacity) {
-                    ParkedRay* dst = Q.slots + slot;
-                    float4* w = reinterpret_cast<float4*>(dst);
-                    w[0] = make_float4(r.ox, r.oy, r.oz, r.tmin);
-                    w[1] = make_float4(r.dx, r.dy, r.dz, r.hit_t);
-                    reinterpret_cast<int4*>(w)[2] = make_int4(r.vx, r.vy, r.vz, r.hit_id);
-                    dst->tlast = r.tlast; dst->steps = r.steps; dst->ray = id;
-                    __threadfence();
-                    *reinterpret_cast<volatile unsigned*>(&dst->ready) = Q.epoch;
-                    id = -1;                                   // whoever takes the slot writes the hit
-                } else {
-                    walk<CellT, -1, false>(r, P, entries, cells, ref_ids, tris);       // queue full: finish here
-                }
+        {
+            int id = tile * 32 + lane;
+            if (id < num_rays) {
+                if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
+                ok = start_ray(r, P, rays, id);
             }
         }
-        if (id >= 0) finish_ray<kPrimId>(r, hits, id);
+        const bool uniform = walk_warp(ok, r, P, entries, cells, ref_ids, tris);
+        if (!uniform && feedback && lane == 0) atomicAdd(feedback, 1);
+        {   // the ray's place in the buffer again (cheaper than keeping it in a register across the march)
+            int id = tile * 32 + lane;
+            if (id < num_rays) {
+                if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
+                finish_ray<kPrimId>(r, hits, id);
+            }
+        }
         __syncwarp();
 #ifdef HGB_TILE_TRACE
         traced_tiles++;
         if (lane == 0 && trace_slot < 8192) { g_tile_trace[3 * trace_slot + 1] = global_ns(); g_tile_trace[3 * trace_slot + 2] = traced_tiles; }
 #endif
         tile = fetch_tile(next_tile, ticket_base, first_dynamic, lane);
-    }
-    if (!Q.capacity) return;
-
-    // ---- service phase: this warp has run out of tiles; it takes parked rays one at a time and finishes each with all
-    // its lanes (split_walk) until every warp has left the tile phase and every parked ray has been taken
-    __threadfence();
-    if (lane == 0) atomicAdd(Q.counters + 2, 1u);
-    const unsigned warps = gridDim.x * (kTileBlock / 32);
-    while (true) {
-        unsigned take = 0;
-        if (lane == 0) take = atomicAdd(Q.counters + 1, 1u);
-        take = __shfl_sync(kAll, take, 0);
-        if (take >= Q.capacity) break;
-        const ParkedRay* src = Q.slots + take;
-        bool have = false;
-        while (true) {
-            if (load_volatile(&src->ready) == Q.epoch) { have = true; break; }
-            if (load_volatile(Q.counters + 2) == warps) {
-                // nobody parks any more: the slot is either filled (and visible) or will never be
-                __threadfence();
-                have = take < min(load_volatile(Q.counters), Q.capacity);
-                break;
-            }
-            __nanosleep(256);
-        }
-        if (!have) break;
-        __threadfence();
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(src) + 0);
-        const float4 b = __ldcg(reinterpret_cast<const float4*>(src) + 1);
-        const int4 c = __ldcg(reinterpret_cast<const int4*>(src) + 2);
-        const int4 d = __ldcg(reinterpret_cast<const int4*>(src) + 3);
-        const SplitResult res = split_walk<CellT>(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.w, c.x, c.y, c.z, __int_as_float(d.x),
-                                                  P, S, entries, cells, ref_ids, tris);
-        if (lane == 0)
-            dev::stg4_stream(hits + d.z, make_float4(__int_as_float(kPrimId ? res.hit_id : d.y + res.steps), res.hit_t, 0.0f, 0.0f));
     }
 }
 
@@ -832,7 +551,7 @@ __device__ __forceinline__ int frame_pixel(const FrameParams& F, int tile, int l
 
 /// Fused frame: generate, trace, shade. One launch, resident warps pulling tiles.
 template <typename CellT, int kMode>
-__global__ void __launch_bounds__(128, 10)
+__global__ void __launch_bounds__(kTileBlock, kTileBlocksPerSm)
 render_tiles(const __grid_constant__ TraversalParams P, const __grid_constant__ FrameParams F,
              const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
              const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
@@ -1011,9 +730,6 @@ struct DeviceState {
     int feedback_mixed = 0, feedback_launches = 0;   // counter values when the current buffer was armed
     bool feedback_armed = false;
     int num_sms = 0;
-    ParkedRay* parked = nullptr;     // straggler queue of tile launches on the default stream
-    unsigned parked_capacity = 0, parked_epoch = 0;
-    unsigned* parked_counters = nullptr;
     // host-buffer frames (traverse_grid_host): one upload stream, one download stream, two traversal streams
     static constexpr int kStreams = 4, kMaxChunks = 64;
     cudaStream_t streams[kStreams] = {};            // 0 = upload, 1 = download, 2 and 3 = traversal
@@ -1044,7 +760,6 @@ DeviceState& device_state() {
         st.stream_tiles[1].word = reinterpret_cast<unsigned*>(st.words + 40);
         st.layout = st.words + 48;
         st.feedback_dev = st.words + 56;
-        st.parked_counters = reinterpret_cast<unsigned*>(st.words + 60);
         HGB_CUDA(cudaHostAlloc(&st.layout_host, 4 * sizeof(int), cudaHostAllocMapped));
         st.layout_host[0] = st.layout_host[1] = st.layout_host[2] = st.layout_host[3] = 0;
         st.feedback_host = st.layout_host + 2;
@@ -1071,18 +786,10 @@ void prepare_streams(DeviceState& st) {
 // 3 (default): 4 for buffers that are (or may be) rasters, 1 once a buffer is known not to be one
 std::atomic<int> g_variant{-1};
 
-// Host-buffer frames: rays per full-size chunk (tuned on B200/PCIe 5: ~350 K rays = 11 MB up, 5.6 MB down)
-std::atomic<int> g_host_frame_chunk{384 * 1024};
-// Host-buffer frames of page-locked raster buffers: 0 = staged through device buffers both ways, 1 = rays staged by the
-// copy engine, hits written by the kernel straight into the caller's host buffer, 2 = one launch that reads the rays
-// from and writes the hits to host memory (cp.async staging hides the PCIe latency)
-std::atomic<int> g_host_frame_mode{0};
-// Host-buffer frames: > 0 = every chunk is this percentage of the rays still to go, 0 = chunks of equal size
-std::atomic<int> g_host_frame_fraction{0};
-// traverse_tiles: parking and split march of stragglers (SplitParams); budget 0 = off
-std::atomic<int> g_split_budget{64}, g_split_voxels{64}, g_split_max_segments{8}, g_split_min_segments{2};
+// Host-buffer frames: rays per full-size chunk (tuned on B200/PCIe 5, profiles/r02_e2e.md: 256 K rays = 8.6 MB up, 4.3 MB down)
+std::atomic<int> g_host_frame_chunk{256 * 1024};
 // rasters smaller than this many rays are traced one thread per ray (re-tiled): a small launch does not fill the resident warps
-std::atomic<int> g_tile_min_rays{512 << 10};
+std::atomic<int> g_tile_min_rays{1280 << 10};      // profiles/r02_traverse_experiments.md: half a 1920x1080 frame is on the line
 
 int traverse_variant() {
     int v = g_variant.load();
@@ -1094,42 +801,19 @@ int traverse_variant() {
     return v;
 }
 
-/// The straggler queue of a launch over `num_rays` rays on the default stream (null capacity: nothing is parked)
-StragglerQueue straggler_queue(DeviceState& st, const TraversalParams& P, int num_rays, cudaStream_t stream) {
-    StragglerQueue Q = {};
-    if (g_split_budget.load() <= 0 || max(P.dims_x, max(P.dims_y, P.dims_z)) > (1 << 21)) return Q;     // pack_voxel
-    const unsigned want = unsigned(std::max(num_rays / 4, 1 << 16));
-    if (want > st.parked_capacity) {
-        if (st.parked) HGB_CUDA(cudaFree(st.parked));
-        HGB_CUDA(cudaMalloc(&st.parked, sizeof(ParkedRay) * size_t(want)));
-        HGB_CUDA(cudaMemsetAsync(st.parked, 0, sizeof(ParkedRay) * size_t(want), stream));
-        st.parked_capacity = want;
-        st.parked_epoch = 0;
-    }
-    if (++st.parked_epoch == 0) {       // wrapped: the flags of 2^32 launches ago must not look fresh
-        HGB_CUDA(cudaMemsetAsync(st.parked, 0, sizeof(ParkedRay) * size_t(st.parked_capacity), stream));
-        st.parked_epoch = 1;
-    }
-    HGB_CUDA(cudaMemsetAsync(st.parked_counters, 0, 4 * sizeof(unsigned), stream));
-    Q.slots = st.parked; Q.capacity = st.parked_capacity; Q.counters = st.parked_counters; Q.epoch = st.parked_epoch;
-    return Q;
-}
-
 /// Enqueues one traversal launch on `stream`: 1 = persistent voting warps (needs `vote_counter`), 4 = resident
 /// warps pulling tiles (needs `ticket`), otherwise one thread per ray; 2 and 4 re-tile by the raster width in
 /// `layout[0]` (device) or `host_width`.
 template <typename CellT, bool kPrimId>
 void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays,
              int variant, const int* layout, int host_width, int* vote_counter, Ticket& ticket, int num_sms, cudaStream_t stream,
-             int* feedback = nullptr, DeviceState* park_in = nullptr) {
+             int* feedback = nullptr) {
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
     const TraversalParams P = params_of(grid);
     if (variant == 4) {
         const int blocks = min(num_sms * kTileBlocksPerSm, round_div(num_rays, kTileBlock));
         traverse_tiles<CellT, kPrimId><<<blocks, kTileBlock, 0, stream>>>(
-            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback,
-            SplitParams{g_split_budget.load(), g_split_voxels.load(), g_split_max_segments.load(), g_split_min_segments.load()},
-            park_in ? straggler_queue(*park_in, P, num_rays, stream) : StragglerQueue{});
+            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback);
         ticket.base += unsigned((num_rays + 31) >> 5);      // one fetch per traced tile (fetch_tile)
         count_launch();
     } else if (variant == 1) {
@@ -1207,7 +891,7 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
     // 5 (experiment): the voting kernel handed rays in tile order
     const bool tiled = variant == 2 || variant == 4 || variant == 5;
     enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant == 5 ? 1 : variant, tiled ? st.layout : nullptr, 0,
-                            st.vote_counter, st.tiles, st.num_sms, 0, feedback, &st);
+                            st.vote_counter, st.tiles, st.num_sms, 0, feedback);
     if (feedback) {
         // copied back after launches 1, 2, 4 and then every 8th: one 8-byte copy in eight launches
         const int tick = ++st.feedback_tick;
@@ -1264,17 +948,6 @@ int host_raster_width(const Ray* rays, int n) {
     return misses > kSpot / 16 ? 0 : width;
 }
 
-/// The address under which the device reaches a page-locked host buffer, or null for pageable memory
-template <typename T>
-T* device_alias(T* host) {
-    void* alias = nullptr;
-    if (cudaHostGetDevicePointer(&alias, const_cast<void*>(static_cast<const void*>(host)), 0) != cudaSuccess) {
-        cudaGetLastError();
-        return nullptr;
-    }
-    return static_cast<T*>(alias);
-}
-
 template <typename CellT, bool kPrimId>
 void launch_host_frame(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* host_rays, Hit* host_hits,
                        int num_rays, Ray* dev_rays, Hit* dev_hits) {
@@ -1289,90 +962,59 @@ void launch_host_frame(const Grid& grid, const CellT* cells, const Tri* tris, co
         width = host_raster_width(host_rays, num_rays);
         variant = width > 0 ? (variant == 2 ? 2 : 4) : (variant == 3 ? 1 : 0);
     }
-    // Page-locked raster frames: the kernel can write the hits into the caller's buffer itself (no download
-    // copies, no tail behind the last traversal), and read the rays from it as well
-    int mode = variant == 4 ? g_host_frame_mode.load() : 0;
-    const Ray* rays_alias = mode == 2 ? device_alias(host_rays) : nullptr;
-    Hit* hits_alias = mode >= 1 ? device_alias(host_hits) : nullptr;
-    if (mode >= 1 && !hits_alias) mode = 0;
-    if (mode == 2 && !rays_alias) mode = 1;
-
     HGB_CUDA(cudaEventRecord(st.frame_start, 0));           // frames are ordered after earlier default-stream work
     for (int i = 0; i < DeviceState::kStreams; i++) HGB_CUDA(cudaStreamWaitEvent(st.streams[i], st.frame_start, 0));
-    if (mode == 2) {
-        enqueue<CellT, kPrimId>(grid, cells, tris, rays_alias, hits_alias, num_rays, variant, nullptr, width,
-                                st.stream_vote_counters[0], st.stream_tiles[0], st.num_sms, st.streams[2]);
-    } else {
-        // Chunks are whole 4-row tile bands of a raster, else whole blocks. Full-size chunks keep the copy
-        // engines busy with few, large transfers; the last one is split 1/2, 1/4, 1/4 because nothing
-        // overlaps the final traversal (+ download).
-        const int granule = width > 0 ? width * kTileH : kBlockThreads;
-        const int chunk = g_host_frame_chunk.load();
-        std::vector<int> sizes;
-        const int fraction = g_host_frame_fraction.load();
-        if (fraction > 0) {
-            // Shrinking chunks: every chunk is `fraction` percent of what is left (never below `chunk` rays): few, large
-            // copies while there is plenty to overlap them with, small ones at the end where nothing hides the last
-            // traversal and download.
-            long long rest = num_rays;
-            while (rest > 0 && int(sizes.size()) < DeviceState::kMaxChunks - 1) {
-                long long want = std::max<long long>(chunk, rest * fraction / 100);
-                want = std::max<long long>(granule, (want + granule - 1) / granule * granule);
-                if (want > rest || rest - want < chunk / 2) want = rest;
-                sizes.push_back(int(want));
-                rest -= want;
-            }
-            if (rest > 0) sizes.push_back(int(rest));
-        } else {
-            long long full = std::max<long long>(granule, (long long)round_div(chunk, granule) * granule);
-            full = std::max<long long>(full, (long long)round_div(round_div(num_rays, DeviceState::kMaxChunks - 4), granule) * granule);
-            long long rest = num_rays;
-            while (rest > full + full / 2) { sizes.push_back(int(full)); rest -= full; }
-            const long long half = std::min<long long>(rest, (long long)round_div(int(rest / 2), granule) * granule);
-            const long long quarter = std::min<long long>(rest - half, (long long)round_div(int(rest / 4), granule) * granule);
-            if (half > 0) sizes.push_back(int(half));
-            if (quarter > 0) sizes.push_back(int(quarter));
-            if (rest - half - quarter > 0) sizes.push_back(int(rest - half - quarter));
-        }
-        cudaStream_t up = st.streams[0], down = st.streams[1];
-        // HGB_FRAME_TRACE=1: time stamps of every chunk's upload, traversal and download (diagnosis only)
-        static const bool trace = std::getenv("HGB_FRAME_TRACE") != nullptr;
-        std::vector<cudaEvent_t> stamps;
-        auto stamp = [&](cudaStream_t on) {
-            if (!trace) return;
-            cudaEvent_t e; HGB_CUDA(cudaEventCreate(&e)); HGB_CUDA(cudaEventRecord(e, on)); stamps.push_back(e);
-        };
+    // Chunks are whole 4-row tile bands of a raster, else whole blocks. Full-size chunks keep the copy
+    // engines busy with few, large transfers; the last one is split 1/2, 1/4, 1/4 because nothing
+    // overlaps the final traversal (+ download).
+    const int granule = width > 0 ? width * kTileH : kBlockThreads;
+    const int chunk = g_host_frame_chunk.load();
+    std::vector<int> sizes;
+    {
+        long long full = std::max<long long>(granule, (long long)round_div(chunk, granule) * granule);
+        full = std::max<long long>(full, (long long)round_div(round_div(num_rays, DeviceState::kMaxChunks - 4), granule) * granule);
+        long long rest = num_rays;
+        while (rest > full + full / 2) { sizes.push_back(int(full)); rest -= full; }
+        const long long half = std::min<long long>(rest, (long long)round_div(int(rest / 2), granule) * granule);
+        const long long quarter = std::min<long long>(rest - half, (long long)round_div(int(rest / 4), granule) * granule);
+        if (half > 0) sizes.push_back(int(half));
+        if (quarter > 0) sizes.push_back(int(quarter));
+        if (rest - half - quarter > 0) sizes.push_back(int(rest - half - quarter));
+    }
+    cudaStream_t up = st.streams[0], down = st.streams[1];
+    // HGB_FRAME_TRACE=1: time stamps of every chunk's upload, traversal and download (diagnosis only)
+    static const bool trace = std::getenv("HGB_FRAME_TRACE") != nullptr;
+    std::vector<cudaEvent_t> stamps;
+    auto stamp = [&](cudaStream_t on) {
+        if (!trace) return;
+        cudaEvent_t e; HGB_CUDA(cudaEventCreate(&e)); HGB_CUDA(cudaEventRecord(e, on)); stamps.push_back(e);
+    };
+    stamp(up);
+    long long begin = 0;
+    for (size_t c = 0; c < sizes.size(); begin += sizes[c], c++) {
+        const int count = sizes[c];
+        cudaStream_t run = st.streams[2 + (c & 1)];      // consecutive traversals may overlap (tails of incoherent chunks)
+        HGB_CUDA(cudaMemcpyAsync(dev_rays + begin, host_rays + begin, sizeof(Ray) * size_t(count), cudaMemcpyHostToDevice, up));
+        HGB_CUDA(cudaEventRecord(st.uploaded[c], up));
         stamp(up);
-        long long begin = 0;
-        for (size_t c = 0; c < sizes.size(); begin += sizes[c], c++) {
-            const int count = sizes[c];
-            cudaStream_t run = st.streams[2 + (c & 1)];      // consecutive traversals may overlap (tails of incoherent chunks)
-            HGB_CUDA(cudaMemcpyAsync(dev_rays + begin, host_rays + begin, sizeof(Ray) * size_t(count), cudaMemcpyHostToDevice, up));
-            HGB_CUDA(cudaEventRecord(st.uploaded[c], up));
-            stamp(up);
-            HGB_CUDA(cudaStreamWaitEvent(run, st.uploaded[c], 0));
-            // mode 3: only the last two chunks write their hits across PCIe themselves (nothing overlaps their download)
-            const bool direct = mode == 1 || (mode == 3 && c + 2 >= sizes.size());
-            enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, (direct ? hits_alias : dev_hits) + begin, count, variant, nullptr, width,
-                                    st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
-            stamp(run);
-            if (!direct) {
-                HGB_CUDA(cudaEventRecord(st.traced[c], run));
-                HGB_CUDA(cudaStreamWaitEvent(down, st.traced[c], 0));
-                HGB_CUDA(cudaMemcpyAsync(host_hits + begin, dev_hits + begin, sizeof(Hit) * size_t(count), cudaMemcpyDeviceToHost, down));
-            }
-            stamp(down);
+        HGB_CUDA(cudaStreamWaitEvent(run, st.uploaded[c], 0));
+        enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, dev_hits + begin, count, variant, nullptr, width,
+                                st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
+        stamp(run);
+        HGB_CUDA(cudaEventRecord(st.traced[c], run));
+        HGB_CUDA(cudaStreamWaitEvent(down, st.traced[c], 0));
+        HGB_CUDA(cudaMemcpyAsync(host_hits + begin, dev_hits + begin, sizeof(Hit) * size_t(count), cudaMemcpyDeviceToHost, down));
+        stamp(down);
+    }
+    if (trace) {
+        HGB_CUDA(cudaDeviceSynchronize());
+        std::fprintf(stderr, "frame trace (ms since the first upload was enqueued): chunk rays uploaded traced downloaded\n");
+        for (size_t c = 0; c < sizes.size(); c++) {
+            float t[3];
+            for (int k = 0; k < 3; k++) HGB_CUDA(cudaEventElapsedTime(&t[k], stamps[0], stamps[1 + 3 * c + k]));
+            std::fprintf(stderr, "  %2zu %8d %7.3f %7.3f %7.3f\n", c, sizes[c], t[0], t[1], t[2]);
         }
-        if (trace) {
-            HGB_CUDA(cudaDeviceSynchronize());
-            std::fprintf(stderr, "frame trace (ms since the first upload was enqueued): chunk rays uploaded traced downloaded\n");
-            for (size_t c = 0; c < sizes.size(); c++) {
-                float t[3];
-                for (int k = 0; k < 3; k++) HGB_CUDA(cudaEventElapsedTime(&t[k], stamps[0], stamps[1 + 3 * c + k]));
-                std::fprintf(stderr, "  %2zu %8d %7.3f %7.3f %7.3f\n", c, sizes[c], t[0], t[1], t[2]);
-            }
-            for (cudaEvent_t e : stamps) cudaEventDestroy(e);
-        }
+        for (cudaEvent_t e : stamps) cudaEventDestroy(e);
     }
     HGB_CUDA(cudaGetLastError());
     for (int i = 0; i < DeviceState::kStreams; i++) {
@@ -1417,11 +1059,11 @@ void launch_frame(const Grid& grid, const CellT* cells, const Tri* tris, const F
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
     const TraversalParams P = params_of(grid);
     const int num_pixels = F.width * F.height;
-    const int blocks = std::min(st.num_sms * 10, round_div(num_pixels, 128));
+    const int blocks = std::min(st.num_sms * kTileBlocksPerSm, round_div(num_pixels, kTileBlock));
     Ticket& t = st.tiles;
-    if (mode == 0)      render_tiles<CellT, 0><<<blocks, 128>>>(P, F, entries, cells, grid.ref_ids, tris, pixels, t.word, t.base);
-    else if (mode == 1) render_tiles<CellT, 1><<<blocks, 128>>>(P, F, entries, cells, grid.ref_ids, tris, pixels, t.word, t.base);
-    else                render_tiles<CellT, 2><<<blocks, 128>>>(P, F, entries, cells, grid.ref_ids, tris, pixels, t.word, t.base);
+    if (mode == 0)      render_tiles<CellT, 0><<<blocks, kTileBlock>>>(P, F, entries, cells, grid.ref_ids, tris, pixels, t.word, t.base);
+    else if (mode == 1) render_tiles<CellT, 1><<<blocks, kTileBlock>>>(P, F, entries, cells, grid.ref_ids, tris, pixels, t.word, t.base);
+    else                render_tiles<CellT, 2><<<blocks, kTileBlock>>>(P, F, entries, cells, grid.ref_ids, tris, pixels, t.word, t.base);
     t.base += unsigned((num_pixels + 31) >> 5);
     count_launch();
     HGB_CUDA(cudaGetLastError());
@@ -1457,14 +1099,8 @@ void render_frame(const Grid& grid, const Tri* tris, const FrameCamera& cam, flo
 
 bool set_traversal_option(const char* key, int value) {
     if (!std::strcmp(key, "traverse_variant")) { g_variant.store(value); return true; }
-    if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk.store(value > 0 ? value : 384 * 1024); return true; }
-    if (!std::strcmp(key, "host_frame_mode")) { g_host_frame_mode.store(value < 0 || value > 3 ? 0 : value); return true; }
-    if (!std::strcmp(key, "host_frame_fraction")) { g_host_frame_fraction.store(value < 0 || value > 90 ? 0 : value); return true; }
-    if (!std::strcmp(key, "split_budget")) { g_split_budget.store(value >= 0 ? value : 64); return true; }
-    if (!std::strcmp(key, "split_voxels")) { g_split_voxels.store(value > 0 ? value : 32); return true; }
-    if (!std::strcmp(key, "split_max_segments")) { g_split_max_segments.store(value > 0 ? min(value, 32) : 8); return true; }
-    if (!std::strcmp(key, "split_min_segments")) { g_split_min_segments.store(value > 0 ? value : 2); return true; }
-    if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (512 << 10)); return true; }
+    if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk.store(value > 0 ? value : 256 * 1024); return true; }
+    if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (1280 << 10)); return true; }
     return false;
 }
 
@@ -1492,10 +1128,5 @@ void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays,
 #ifdef HGB_TILE_TRACE
 extern "C" __attribute__((visibility("default"))) int hgb_debug_tile_trace(long long* out) {
     return cudaMemcpyFromSymbol(out, hagrid::g_tile_trace, sizeof(long long) * 3 * 8192) == cudaSuccess ? 0 : -1;
-}
-extern "C" __attribute__((visibility("default"))) int hgb_debug_split_stats(unsigned long long* out, int reset) {
-    if (cudaMemcpyFromSymbol(out, hagrid::g_split_stats, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
-    if (reset) { unsigned long long zero[8] = {}; cudaMemcpyToSymbol(hagrid::g_split_stats, zero, sizeof(zero)); }
-    return 0;
 }
 #endif

@@ -242,8 +242,7 @@ def sponza_reference(ref_lib):
 
 def test_c2_headline_buffers_match_the_reference_in_every_variant(lib, sponza, sponza_reference):
     """BASELINE.json C2, the exact buffers bench.py times: grid byte-identical to the reference's, prim ids, t and step
-    counts bit-identical for the default view and the long-axis view, in all five kernel selections and with the
-    tile kernel's ray staging on and off."""
+    counts bit-identical for the default view and the long-axis view, in all five kernel selections."""
     tris, sc, _ = sponza
     R = sponza_reference
     info, arrays = dump(sc)
@@ -253,16 +252,15 @@ def test_c2_headline_buffers_match_the_reference_in_every_variant(lib, sponza, s
             want_ids, want_steps = R["want"][name]
             assert (want_ids["id"] >= 0).mean() > 0.9
             for v in VARIANTS:
-                for stage in ((0, 1) if v in (3, 4) else (1,)):
-                    lib.set_option("traverse_variant", v); lib.set_option("tile_stage", stage)
-                    assert _bit_equal(sc.trace(rays, HIT_PRIM_ID), want_ids), (name, v, stage)
-                    assert _bit_equal(sc.trace(rays, HIT_STEPS), want_steps), (name, v, stage)
+                lib.set_option("traverse_variant", v)
+                assert _bit_equal(sc.trace(rays, HIT_PRIM_ID), want_ids), (name, v)
+                assert _bit_equal(sc.trace(rays, HIT_STEPS), want_steps), (name, v)
     finally:
-        lib.set_option("traverse_variant", 3); lib.set_option("tile_stage", 1)
+        lib.set_option("traverse_variant", 3)
 
 
-def test_c2_host_buffer_frames_match_the_reference_in_every_mode(lib, sponza, sponza_reference):
-    """The e2e call of bench.py (hgb_traverse_grid_host) with page-locked and pageable buffers, every frame mode."""
+def test_c2_host_buffer_frames_match_the_reference(lib, sponza, sponza_reference):
+    """The e2e call of bench.py (hgb_traverse_grid_host) with page-locked and pageable buffers, several chunk sizes."""
     import torch
     tris, sc, _ = sponza
     rays = sponza_reference["views"]["default"]
@@ -271,16 +269,15 @@ def test_c2_host_buffer_frames_match_the_reference_in_every_mode(lib, sponza, sp
     pinned_rays = torch.from_numpy(rays.view(np.float32).reshape(n, 8)).pin_memory()
     pinned_hits = torch.empty((n, 4), dtype=torch.float32).pin_memory()
     try:
-        for mode in (0, 1, 2):
-            for stage in (0, 1):
-                lib.set_option("host_frame_mode", mode); lib.set_option("tile_stage", stage)
-                pinned_hits.zero_()
-                lib.check(lib.dll.hgb_traverse_grid_host(sc._h, pinned_rays.data_ptr(), pinned_hits.data_ptr(), n, HIT_PRIM_ID), "frame")
-                got = pinned_hits.numpy().view(want.dtype).reshape(-1)
-                assert _bit_equal(got, want), (mode, stage)
-                assert _bit_equal(sc.traverse_host(rays, HIT_PRIM_ID), want), ("pageable", mode, stage)
+        for chunk in (0, 64 << 10, 1 << 20, 1 << 30):
+            lib.set_option("host_frame_chunk_rays", chunk)
+            pinned_hits.zero_()
+            lib.check(lib.dll.hgb_traverse_grid_host(sc._h, pinned_rays.data_ptr(), pinned_hits.data_ptr(), n, HIT_PRIM_ID), "frame")
+            got = pinned_hits.numpy().view(want.dtype).reshape(-1)
+            assert _bit_equal(got, want), chunk
+            assert _bit_equal(sc.traverse_host(rays, HIT_PRIM_ID), want), ("pageable", chunk)
     finally:
-        lib.set_option("host_frame_mode", 0); lib.set_option("tile_stage", 1)
+        lib.set_option("host_frame_chunk_rays", 0)
 
 
 def test_c3_headline_buffer_matches_the_reference_in_every_variant(lib, sponza, sponza_reference):

@@ -1,5 +1,6 @@
-"""Round-2 traversal experiments on one B200 (run under gpurun): every switch of the tile kernel and of the host-buffer
-frame against the reference rebuilt for sm_100a, same buffers, hits compared bit for bit.
+"""Round-2 traversal measurements on one B200 (run under gpurun): the tile kernel and the host-buffer frame against the
+reference rebuilt for sm_100a, same buffers, hits compared bit for bit (the switches of the rejected experiments of
+profiles/r02_traverse_experiments.md went with their code).
 usage: gpu_r02_traverse.py [c2] [c5] [e2e] [shards]   (default: all)
 Timing as in bench.py: CUDA event pair per launch on the legacy stream, 256 MiB memset between launches (L2 flushed)."""
 import json
@@ -72,7 +73,7 @@ def compare_buffer(tag, sr, sm, rays, settings, iters=30):
     return want
 
 
-SETTINGS = {"plain": {"tile_pipeline": 0}, "pipelined": {"tile_pipeline": 1}}
+SETTINGS = {"default": {}}
 
 if "c2" in what or "e2e" in what or "shards" in what:
     tris = scenes.sponza262k()
@@ -88,8 +89,7 @@ if "c2" in what or "e2e" in what or "shards" in what:
             idx = sharding.interleaved_bands(primary.shape[0], 0, world, sharding.raster_granule(W))
             part = np.ascontiguousarray(primary[idx])
             compare_buffer(f"c2_shard_1of{world}", sr, sm, part,
-                           {"per_thread": {"tile_min_rays": 1 << 30}, "tiles": {"tile_pipeline": 0, "tile_min_rays": 0},
-                            "tiles_pipelined": {"tile_pipeline": 1, "tile_min_rays": 0}}, 30)
+                           {"per_thread": {"tile_min_rays": 1 << 30}, "tiles": {"tile_min_rays": 0}}, 30)
         mine.set_option("tile_min_rays", -1)
     if "e2e" in what:
         n = primary.shape[0]
@@ -99,17 +99,17 @@ if "c2" in what or "e2e" in what or "shards" in what:
         res = {}
         r = timed(lambda: ref.check(ref.dll.hgb_traverse_grid_host(sr._h, h_rays.data_ptr(), h_hits.data_ptr(), n, HIT_PRIM_ID), "f"), 20, 3)
         res["reference"] = r
-        for mode in (0, 1):
+        for mode in (0,):
             for stage in (0,):
-                for chunk in (224, 256, 288):
-                    mine.set_option("host_frame_mode", mode); mine.set_option("host_frame_chunk_rays", chunk * 1024)
+                for chunk in (224, 256, 288, 384):
+                    mine.set_option("host_frame_chunk_rays", chunk * 1024)
                     h_hits.zero_()
                     t = timed(lambda: mine.check(mine.dll.hgb_traverse_grid_host(sm._h, h_rays.data_ptr(), h_hits.data_ptr(), n, HIT_PRIM_ID), "f"), 20, 3)
                     t["identical"] = bool(np.array_equal(h_hits.numpy().view(np.int32)[:, 0], want["id"]) and
                                           np.array_equal(h_hits.numpy()[:, 1], want["t"]))
                     t["speedup"] = round(r["ms_mean"] / t["ms_mean"], 3)
                     res[f"mode{mode}_stage{stage}_chunk{chunk}K"] = t
-        mine.set_option("host_frame_mode", 0); mine.set_option("host_frame_chunk_rays", 0)
+        mine.set_option("host_frame_chunk_rays", 0)
         out["c2_e2e"] = res
         print("c2_e2e", json.dumps(res), flush=True)
     sr.close(); sm.close()
