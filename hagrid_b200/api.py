@@ -82,6 +82,11 @@ _SIGNATURES = {
     "hgb_render_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hgb_generate_bounce_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_uint,
                                           C.c_void_p]),
+    "hgb_generate_bounce_rays_keyed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_uint,
+                                                C.c_void_p, C.c_void_p]),
+    "hgb_count_hits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "hgb_trace_two_waves_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_uint,
+                                          C.c_void_p, C.c_void_p]),
     "hgb_save_image": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "hgb_rays_file_count": (C.c_longlong, [C.c_char_p]),
     "hgb_load_rays": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_float, C.c_float, C.c_void_p]),
@@ -312,6 +317,24 @@ class Scene:
         self.lib.check(self.lib.dll.hgb_generate_bounce_rays(self._h, dev_rays, dev_hits, num_rays, offset, tmax,
                                                              seed & 0xFFFFFFFF, dev_out if dev_out else dev_rays),
                        "generate_bounce_rays")
+
+    def bounce_rays_keyed(self, dev_rays, dev_hits, num_rays: int, offset: float, tmax: float, seed: int, dev_keys, dev_out=None):
+        """Second wave of a shard: `dev_keys` = the rays' indices in the whole frame (hgb_generate_bounce_rays_keyed)."""
+        self.lib.check(self.lib.dll.hgb_generate_bounce_rays_keyed(self._h, _ptr(dev_rays), _ptr(dev_hits), num_rays, offset, tmax,
+                                                                   seed & 0xFFFFFFFF, _ptr(dev_keys),
+                                                                   _ptr(dev_out) if dev_out is not None else _ptr(dev_rays)),
+                       "generate_bounce_rays_keyed")
+
+    def count_hits(self, dev_hits, num_hits: int, dev_counters):
+        """dev_counters (two uint64, device) += [hits with id >= 0, sum of id + 1] (hgb_count_hits)."""
+        self.lib.check(self.lib.dll.hgb_count_hits(self._h, _ptr(dev_hits), num_hits, _ptr(dev_counters)), "count_hits")
+
+    def trace_two_waves_host(self, host_rays, num_rays: int, dev_keys, offset: float, tmax: float, seed: int, host_hits_primary,
+                             host_hits_bounce):
+        """One two-wave frame with host buffers (hgb_trace_two_waves_host)."""
+        self.lib.check(self.lib.dll.hgb_trace_two_waves_host(self._h, _ptr(host_rays), num_rays, _ptr(dev_keys), offset, tmax,
+                                                             seed & 0xFFFFFFFF, _ptr(host_hits_primary), _ptr(host_hits_bounce)),
+                       "trace_two_waves_host")
 
     def bounce_rays(self, rays: np.ndarray, hits: np.ndarray, offset: float, tmax: float, seed: int) -> np.ndarray:
         """Host-array convenience over bounce_rays_device: `hits` are primitive-id hits of `rays`."""

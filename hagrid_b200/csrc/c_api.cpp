@@ -45,6 +45,8 @@ void traverse_grid_pid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* 
 void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays);
 void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays, Hit* host_hits, int num_rays,
                         Ray* dev_rays, Hit* dev_hits, bool prim_ids);
+void traverse_grid_to_host(const Grid& grid, const Tri* tris, const Ray* dev_rays, Hit* dev_hits, Hit* host_hits, int num_rays,
+                           bool prim_ids);
 bool set_traversal_option(const char* key, int value);
 unsigned long long kernel_launch_count();
 void trim_device_pool();
@@ -434,6 +436,55 @@ int hgb_generate_bounce_rays(hgb_scene* s, const void* dev_rays, const void* dev
 #else
     generate_bounce_rays(s->tris, s->num_tris, static_cast<const Ray*>(dev_rays), static_cast<const Hit*>(dev_hits),
                          num_rays, offset, tmax, seed, static_cast<Ray*>(dev_out));
+    return 0;
+#endif
+}
+
+int hgb_generate_bounce_rays_keyed(hgb_scene* s, const void* dev_rays, const void* dev_hits, int num_rays, float offset,
+                                   float tmax, unsigned seed, const void* dev_keys, void* dev_out) {
+    if (!bind(s)) return -1;
+    if (num_rays < 0 || (num_rays > 0 && (!dev_rays || !dev_hits || !dev_out))) return fail("generate_bounce_rays_keyed: bad argument");
+    if (!s->tris) return fail("generate_bounce_rays_keyed: the scene has no triangles");
+#ifdef HGB_REFERENCE_BUILD
+    (void)offset; (void)tmax; (void)seed; (void)dev_keys;
+    return fail("generate_bounce_rays_keyed: the reference has no second-wave ray generation");
+#else
+    generate_bounce_rays(s->tris, s->num_tris, static_cast<const Ray*>(dev_rays), static_cast<const Hit*>(dev_hits),
+                         num_rays, offset, tmax, seed, static_cast<Ray*>(dev_out), static_cast<const int*>(dev_keys));
+    return 0;
+#endif
+}
+
+int hgb_count_hits(hgb_scene* s, const void* dev_hits, int num_hits, void* dev_counters) {
+    if (!bind(s)) return -1;
+    if (num_hits < 0 || (num_hits > 0 && !dev_hits) || !dev_counters) return fail("count_hits: bad argument");
+#ifdef HGB_REFERENCE_BUILD
+    return fail("count_hits: not part of the reference");
+#else
+    count_hits(static_cast<const Hit*>(dev_hits), num_hits, static_cast<unsigned long long*>(dev_counters));
+    return 0;
+#endif
+}
+
+int hgb_trace_two_waves_host(hgb_scene* s, const void* host_rays, int num_rays, const void* dev_keys, float offset, float tmax,
+                             unsigned seed, void* host_hits_primary, void* host_hits_bounce) {
+    if (!bind(s)) return -1;
+    if (!s->grid.entries) return fail("trace_two_waves_host: no grid");
+    if (!setup_matches(s)) return fail("trace_two_waves_host: hgb_setup_traversal was not called for this grid");
+    if (num_rays < 0 || (num_rays > 0 && (!host_rays || !host_hits_primary || !host_hits_bounce))) return fail("trace_two_waves_host: bad argument");
+    if (num_rays == 0) return 0;
+#ifdef HGB_REFERENCE_BUILD
+    (void)dev_keys; (void)offset; (void)tmax; (void)seed;
+    return fail("trace_two_waves_host: the reference has no second-wave ray generation");
+#else
+    reserve_frame(s, num_rays);
+    // first wave: upload, trace, download in overlapping chunks; the rays and their hits stay in the staging buffers
+    traverse_grid_host(s->grid, s->tris, static_cast<const Ray*>(host_rays), static_cast<Hit*>(host_hits_primary), num_rays,
+                       s->frame_rays, s->frame_hits, true);
+    // second wave: made on the device from what is resident (in place), traced, downloaded chunk by chunk
+    generate_bounce_rays(s->tris, s->num_tris, s->frame_rays, s->frame_hits, num_rays, offset, tmax, seed, s->frame_rays,
+                         static_cast<const int*>(dev_keys));
+    traverse_grid_to_host(s->grid, s->tris, s->frame_rays, s->frame_hits, static_cast<Hit*>(host_hits_bounce), num_rays, true);
     return 0;
 #endif
 }

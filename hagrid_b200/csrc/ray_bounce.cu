@@ -4,6 +4,8 @@
 // with the same operation order. Every float operation is a single IEEE
 // round-to-nearest instruction (no contraction, no approximate reciprocal, no trigonometry), so the CPU
 // restatement and this kernel agree bit for bit.
+#include <algorithm>
+
 #include "hgb_api.h"
 #include "runtime.h"
 
@@ -28,7 +30,7 @@ constexpr int kDiskTries = 8;
 
 __global__ void __launch_bounds__(256)
 bounce_rays(const Tri* __restrict__ tris, int num_tris, const Ray* rays, const Hit* __restrict__ hits, int num_rays,
-            float offset, float tmax, uint32_t seed, Ray* out) {
+            float offset, float tmax, uint32_t seed, const int* __restrict__ keys, Ray* out) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= num_rays) return;
     const float4 a = reinterpret_cast<const float4*>(rays + i)[0];     // org, tmin
@@ -55,7 +57,9 @@ bounce_rays(const Tri* __restrict__ tris, int num_tris, const Ray* rays, const H
     const float py = __fadd_rn(__fadd_rn(a.y, __fmul_rn(b.y, h.y)), __fmul_rn(ny, offset));
     const float pz = __fadd_rn(__fadd_rn(a.z, __fmul_rn(b.z, h.y)), __fmul_rn(nz, offset));
     // uniform point of the unit disk by rejection, lifted to the hemisphere: cosine-weighted direction
-    const uint32_t base = mix32(seed ^ mix32(uint32_t(i)));
+    // the random stream belongs to the ray, not to its place in this buffer: a shard of a frame passes the rays' indices
+    // in the whole frame as keys and gets the rays the unsharded frame would get
+    const uint32_t base = mix32(seed ^ mix32(uint32_t(keys ? __ldg(keys + i) : i)));
     float dx = 0.0f, dy = 0.0f, s = 0.0f;
     for (int k = 0; k < kDiskTries; k++) {
         const float x = __fsub_rn(__fmul_rn(2.0f, draw(base, 2 * k)), 1.0f);
@@ -80,12 +84,46 @@ bounce_rays(const Tri* __restrict__ tris, int num_tris, const Ray* rays, const H
     dst[1] = make_float4(ox, oy, oz, tmax);
 }
 
+/// counters[0] += hits that name a primitive (id >= 0), counters[1] += sum of (id + 1): the per-frame figures a sharded
+/// frame all-reduces. One 16-byte load per hit, a warp reduction, two atomics per block.
+__global__ void __launch_bounds__(256)
+count_hits_kernel(const Hit* __restrict__ hits, int num_hits, unsigned long long* __restrict__ counters) {
+    unsigned long long found = 0, sum = 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < num_hits; i += gridDim.x * 256) {
+        const int id = __float_as_int(__ldg(reinterpret_cast<const float4*>(hits) + i).x);
+        found += id >= 0;
+        sum += (unsigned long long)(long long)(id + 1);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        found += __shfl_xor_sync(0xFFFFFFFFu, found, d);
+        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    }
+    __shared__ unsigned long long part[2][8];
+    if ((threadIdx.x & 31) == 0) { part[0][threadIdx.x >> 5] = found; part[1][threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned long long total = 0;
+        for (int w = 0; w < 8; w++) total += part[threadIdx.x][w];
+        atomicAdd(counters + threadIdx.x, total);
+    }
+}
+
 } // namespace
 
 void generate_bounce_rays(const Tri* tris, int num_tris, const Ray* rays, const Hit* hits, int num_rays,
-                          float offset, float tmax, unsigned seed, Ray* out) {
+                          float offset, float tmax, unsigned seed, Ray* out, const int* keys) {
     if (num_rays <= 0) return;
-    bounce_rays<<<(num_rays + 255) / 256, 256>>>(tris, num_tris, rays, hits, num_rays, offset, tmax, seed, out); count_launch();
+    bounce_rays<<<(num_rays + 255) / 256, 256>>>(tris, num_tris, rays, hits, num_rays, offset, tmax, seed, keys, out); count_launch();
+    HGB_CUDA(cudaGetLastError());
+}
+
+void count_hits(const Hit* hits, int num_hits, unsigned long long* counters) {
+    if (num_hits <= 0) return;
+    int sms = 0, dev = 0;
+    HGB_CUDA(cudaGetDevice(&dev));
+    HGB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = std::min((num_hits + 255) / 256, sms * 8);
+    count_hits_kernel<<<blocks, 256>>>(hits, num_hits, counters); count_launch();
     HGB_CUDA(cudaGetLastError());
 }
 

@@ -616,11 +616,10 @@ traverse_voting(const __grid_constant__ TraversalParams P,
                 const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                 const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                 const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
-                int* __restrict__ next_ray, const int* __restrict__ layout, int host_width) {
+                int* __restrict__ next_ray) {
     constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
     constexpr unsigned kAll = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    const int width = layout ? __ldg(layout) : host_width;      // > 0: rays are handed out in 8x4 tile order
 
     RayState r;
     int   ray_id = -1;          // -1: lane is idle
@@ -647,9 +646,8 @@ traverse_voting(const __grid_constant__ TraversalParams P,
         if (idle == kAll && drained) break;
         if (!drained && __popc(idle) >= kVoteRefillMinLanes) {
             if (ray_id < 0) {
-                int id = pool + __popc(idle & ((1u << lane) - 1u));
+                const int id = pool + __popc(idle & ((1u << lane) - 1u));
                 if (id < pool_end) {
-                    if (width > 0) id = tiled_ray_index(id, width);
                     if (start_ray(r, P, rays, id)) ray_id = id;
                     else finish_ray<kPrimId>(r, hits, id);
                 }
@@ -719,16 +717,25 @@ struct DeviceState {
     int* words = nullptr;            // 256 bytes of device memory, one 32-byte sector per word in use (below)
     int* vote_counter = nullptr;     // ray counter of the persistent voting kernel (reset before every launch)
     Ticket tiles;                    // tile counter of traverse_tiles / render_tiles on the default stream
-    int* layout = nullptr;           // [0] = raster width found by detect_raster (0 = none)
-    int* layout_host = nullptr;      // pinned, mapped copy of layout[0]; -1 = detection still in flight
-    const void* seen_rays = nullptr; // buffer the layout belongs to
-    int seen_count = -1;
-    int seen_class = -1;             // -1: detection in flight, 0: incoherent, > 0: raster of that width
-    int* feedback_host = nullptr;    // pinned copy of feedback_dev, refreshed by an 8-byte async copy every few launches
-    int* feedback_dev = nullptr;     // device: [0] mixed-octant warps, [1] launches of traverse_tiles (see there)
-    int  feedback_tick = 0;
-    int feedback_mixed = 0, feedback_launches = 0;   // counter values when the current buffer was armed
-    bool feedback_armed = false;
+    // What is known about the ray buffers traced lately ((address, count) -> raster width or incoherent). A frame loop
+    // alternates between a few buffers (primary rays, second wave, ...): each keeps its own answer, its own look-ahead
+    // word and its own feedback counters, so that switching buffers costs no new look and no host synchronisation.
+    struct SeenBuffer {
+        const void* rays = nullptr;
+        int count = -1;
+        int cls = -1;                // -1: first look in flight, 0: incoherent, > 0: raster of that width
+        int* layout = nullptr;       // device: [0] = raster width found by detect_raster (0 = none)
+        int* feedback_dev = nullptr; // device: [0] mixed-octant warps, [1] launches of traverse_tiles (see there)
+        int* host = nullptr;         // pinned, mapped: [0] copy of layout[0] (-1 = look in flight), [2..3] copy of feedback_dev
+        int  feedback_tick = 0;
+        int  feedback_mixed = 0, feedback_launches = 0;   // counter values when the buffer was armed
+        bool feedback_armed = false;
+        unsigned long long used = 0; // launch number of the last use (least recently used entry is replaced)
+    };
+    static constexpr int kSeenBuffers = 4;
+    SeenBuffer seen[kSeenBuffers];
+    unsigned long long launches = 0;
+    int* seen_host = nullptr;        // pinned block behind seen[].host
     int num_sms = 0;
     // host-buffer frames (traverse_grid_host): one upload stream, one download stream, two traversal streams
     static constexpr int kStreams = 4, kMaxChunks = 64;
@@ -758,11 +765,13 @@ DeviceState& device_state() {
         st.stream_tiles[0].word = reinterpret_cast<unsigned*>(st.words + 24);
         st.stream_vote_counters[1] = st.words + 32;
         st.stream_tiles[1].word = reinterpret_cast<unsigned*>(st.words + 40);
-        st.layout = st.words + 48;
-        st.feedback_dev = st.words + 56;
-        HGB_CUDA(cudaHostAlloc(&st.layout_host, 4 * sizeof(int), cudaHostAllocMapped));
-        st.layout_host[0] = st.layout_host[1] = st.layout_host[2] = st.layout_host[3] = 0;
-        st.feedback_host = st.layout_host + 2;
+        HGB_CUDA(cudaHostAlloc(&st.seen_host, DeviceState::kSeenBuffers * 4 * sizeof(int), cudaHostAllocMapped));
+        for (int i = 0; i < DeviceState::kSeenBuffers; i++) {
+            st.seen[i].layout = st.words + 48 + 4 * i;
+            st.seen[i].feedback_dev = st.words + 48 + 4 * i + 2;
+            st.seen[i].host = st.seen_host + 4 * i;
+            for (int k = 0; k < 4; k++) st.seen[i].host[k] = 0;
+        }
         HGB_CUDA(cudaDeviceGetAttribute(&st.num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     return st;
@@ -821,7 +830,7 @@ void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* r
         // every warp reserves two blocks of rays up front: no more warps than there are blocks
         const int blocks = max(1, min(num_sms * kVoteBlocksPerSm, round_div(num_rays, 2 * kVoteBlock * (kBlockThreads / 32))));
         traverse_voting<CellT, kPrimId><<<blocks, kBlockThreads, 0, stream>>>(
-            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, vote_counter, layout, host_width); count_launch();
+            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, vote_counter); count_launch();
     } else {
         traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128, 0, stream>>>(
             P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width); count_launch();
@@ -835,68 +844,78 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
     std::lock_guard<std::mutex> guard(st.lock);
     int variant = traverse_variant();
     int* feedback = nullptr;
-    if (variant >= 2 && variant <= 5) {
+    DeviceState::SeenBuffer* buf = nullptr;
+    if (variant >= 2 && variant <= 4) {
         // What kind of buffer is this? A new one (other address or size) is looked at on the device before its
         // first launch; the answer is remembered on the host.
         // A buffer known as a raster is not looked at again — the tile kernel reports when its contents stop
         // behaving like one (feedback words) — and a buffer known as incoherent is looked at before every
         // launch (a 10 us kernel in front of one that takes several hundred): callers reuse ray buffers.
-        volatile int* answer = st.layout_host;
-        volatile int* fb = st.feedback_host;
-        const bool same = rays == st.seen_rays && num_rays == st.seen_count;
-        if (!same) { st.seen_class = -1; st.feedback_armed = false; }
-        else if (st.seen_class < 0 && *answer >= 0) st.seen_class = *answer;            // the first look has finished
-        else if (st.seen_class == 0 && *answer > 0) st.seen_class = *answer;            // the latest look found a raster again
-        else if (st.seen_class > 0 && st.feedback_armed) {
+        st.launches++;
+        for (auto& e : st.seen)
+            if (e.rays == rays && e.count == num_rays) buf = &e;
+        const bool same = buf != nullptr;
+        if (!same) {
+            buf = &st.seen[0];
+            for (auto& e : st.seen)
+                if (e.used < buf->used) buf = &e;
+            buf->cls = -1; buf->feedback_armed = false;
+        }
+        buf->used = st.launches;
+        volatile int* answer = buf->host;
+        volatile int* fb = buf->host + 2;
+        if (!same) ;                                                          // nothing known yet
+        else if (buf->cls < 0 && *answer >= 0) buf->cls = *answer;            // the first look has finished
+        else if (buf->cls == 0 && *answer > 0) buf->cls = *answer;            // the latest look found a raster again
+        else if (buf->cls > 0 && buf->feedback_armed) {
             // the launches reported since the last look
             const int now_mixed = fb[0], now_launches = fb[1];
-            const int mixed = now_mixed - st.feedback_mixed, launches = now_launches - st.feedback_launches;
-            st.feedback_mixed = now_mixed; st.feedback_launches = now_launches;
+            const int mixed = now_mixed - buf->feedback_mixed, launches = now_launches - buf->feedback_launches;
+            buf->feedback_mixed = now_mixed; buf->feedback_launches = now_launches;
             const int tiles = (num_rays + 31) / 32;
             if (launches > 0 && (long long)mixed * 4 > (long long)launches * tiles) {     // most warps mixed: not camera rays any more
-                st.seen_class = 0;
-                st.feedback_armed = false;
+                buf->cls = 0;
+                buf->feedback_armed = false;
                 *answer = 0;
             }
         }
-        if (!same || st.seen_class == 0) {
+        if (!same || buf->cls == 0) {
             *answer = -1;
             int* host_alias = nullptr;
-            HGB_CUDA(cudaHostGetDevicePointer(&host_alias, st.layout_host, 0));
-            detect_raster<<<1, 256>>>(rays, num_rays, st.layout, host_alias); count_launch();
+            HGB_CUDA(cudaHostGetDevicePointer(&host_alias, buf->host, 0));
+            detect_raster<<<1, 256>>>(rays, num_rays, buf->layout, host_alias); count_launch();
             if (!same) {
                 // a buffer never seen before: wait for the answer (about 10 us, once per buffer) instead of
                 // tracing its first frame with a kernel that may be the wrong one by a factor of 1.7
                 HGB_CUDA(cudaStreamSynchronize(0));
-                st.seen_class = *answer;
+                buf->cls = *answer;
             }
-            st.seen_rays = rays;
-            st.seen_count = num_rays;
+            buf->rays = rays;
+            buf->count = num_rays;
         }
         if (variant == 3) {
-            // small buffers do not fill the resident-warp kernels (5 920 warps on 148 SMs): one thread per ray then
-            if (st.seen_class == 0) variant = num_rays < (128 << 10) ? 0 : 1;
-            else                    variant = num_rays < g_tile_min_rays.load() ? 2 : 4;
+            // small buffers do not fill the resident-warp kernels (7 104 warps on 148 SMs): one thread per ray then
+            if (buf->cls == 0) variant = num_rays < (128 << 10) ? 0 : 1;
+            else               variant = num_rays < g_tile_min_rays.load() ? 2 : 4;
         }
-        if (variant == 4 && st.seen_class > 0) {
-            feedback = st.feedback_dev;
-            if (!st.feedback_armed) {
+        if (variant == 4 && buf->cls > 0) {
+            feedback = buf->feedback_dev;
+            if (!buf->feedback_armed) {
                 // fresh baseline: counters restart from zero for this buffer
-                HGB_CUDA(cudaMemsetAsync(st.feedback_dev, 0, 2 * sizeof(int), 0));
-                st.feedback_host[0] = st.feedback_host[1] = 0;
-                st.feedback_mixed = 0; st.feedback_launches = 0; st.feedback_armed = true; st.feedback_tick = 0;
+                HGB_CUDA(cudaMemsetAsync(buf->feedback_dev, 0, 2 * sizeof(int), 0));
+                buf->host[2] = buf->host[3] = 0;
+                buf->feedback_mixed = 0; buf->feedback_launches = 0; buf->feedback_armed = true; buf->feedback_tick = 0;
             }
         }
     }
-    // 5 (experiment): the voting kernel handed rays in tile order
-    const bool tiled = variant == 2 || variant == 4 || variant == 5;
-    enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant == 5 ? 1 : variant, tiled ? st.layout : nullptr, 0,
+    const bool tiled = variant == 2 || variant == 4;
+    enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, tiled && buf ? buf->layout : nullptr, 0,
                             st.vote_counter, st.tiles, st.num_sms, 0, feedback);
     if (feedback) {
         // copied back after launches 1, 2, 4 and then every 8th: one 8-byte copy in eight launches
-        const int tick = ++st.feedback_tick;
+        const int tick = ++buf->feedback_tick;
         if (tick <= 2 || (tick & 3) == 0 && (tick == 4 || (tick & 7) == 0))
-            HGB_CUDA(cudaMemcpyAsync(st.feedback_host, st.feedback_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, 0));
+            HGB_CUDA(cudaMemcpyAsync(buf->host + 2, buf->feedback_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, 0));
     }
     HGB_CUDA(cudaGetLastError());
 }
@@ -1024,6 +1043,37 @@ void launch_host_frame(const Grid& grid, const CellT* cells, const Tri* tris, co
     for (int i = 0; i < DeviceState::kStreams; i++) HGB_CUDA(cudaStreamSynchronize(st.streams[i]));   // hits are in host memory
 }
 
+/// Device-resident rays, hits wanted in host memory (the second wave of a two-wave frame: its rays were made on the
+/// device): the buffer is traced in chunks on the default stream and every chunk's hits start their way to the host
+/// as soon as it is traced. Returns when `host_hits` is complete.
+template <typename CellT, bool kPrimId>
+void launch_to_host(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* dev_rays, Hit* dev_hits, Hit* host_hits, int num_rays) {
+    if (num_rays <= 0) return;
+    DeviceState& st = device_state();
+    std::lock_guard<std::mutex> guard(st.lock);
+    prepare_streams(st);
+    cudaStream_t down = st.streams[1];
+    HGB_CUDA(cudaEventRecord(st.frame_start, 0));
+    HGB_CUDA(cudaStreamWaitEvent(down, st.frame_start, 0));
+    constexpr int kChunks = 4;
+    const long long step = ((long long)round_div(num_rays, kChunks) + kBlockThreads - 1) / kBlockThreads * kBlockThreads;
+    int c = 0;
+    for (long long begin = 0; begin < num_rays; begin += step, c++) {
+        const int count = int(std::min<long long>(step, num_rays - begin));
+        // second-wave rays are incoherent by construction: no look at their layout
+        int variant = traverse_variant();
+        if (variant == 3) variant = count < (128 << 10) ? 0 : 1;
+        else if (variant != 1) variant = 0;
+        enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, dev_hits + begin, count, variant, nullptr, 0,
+                                st.vote_counter, st.tiles, st.num_sms, 0);
+        HGB_CUDA(cudaEventRecord(st.traced[c], 0));
+        HGB_CUDA(cudaStreamWaitEvent(down, st.traced[c], 0));
+        HGB_CUDA(cudaMemcpyAsync(host_hits + begin, dev_hits + begin, sizeof(Hit) * size_t(count), cudaMemcpyDeviceToHost, down));
+    }
+    HGB_CUDA(cudaGetLastError());
+    HGB_CUDA(cudaStreamSynchronize(down));
+}
+
 template <bool kPrimId>
 void dispatch(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
     if (grid.small_cells) launch<SmallCell, kPrimId>(grid, grid.small_cells, tris, rays, hits, num_rays);
@@ -1110,6 +1160,17 @@ void traverse_grid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits
 
 void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
     dispatch<true>(grid, tris, rays, hits, num_rays);
+}
+
+void traverse_grid_to_host(const Grid& grid, const Tri* tris, const Ray* dev_rays, Hit* dev_hits, Hit* host_hits, int num_rays,
+                           bool prim_ids) {
+    if (grid.small_cells) {
+        if (prim_ids) launch_to_host<SmallCell, true>(grid, grid.small_cells, tris, dev_rays, dev_hits, host_hits, num_rays);
+        else          launch_to_host<SmallCell, false>(grid, grid.small_cells, tris, dev_rays, dev_hits, host_hits, num_rays);
+    } else {
+        if (prim_ids) launch_to_host<Cell, true>(grid, grid.cells, tris, dev_rays, dev_hits, host_hits, num_rays);
+        else          launch_to_host<Cell, false>(grid, grid.cells, tris, dev_rays, dev_hits, host_hits, num_rays);
+    }
 }
 
 void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays, Hit* host_hits, int num_rays,

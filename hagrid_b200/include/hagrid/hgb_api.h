@@ -37,6 +37,12 @@ void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, 
 void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays, Hit* host_hits, int num_rays,
                         Ray* dev_rays, Hit* dev_hits, bool prim_ids);
 
+/// Device-resident rays whose hits are wanted in host memory (the second wave of a frame: its rays were made on the
+/// device by generate_bounce_rays): traced in chunks, every chunk's hits travel to the host while the next chunk is
+/// traced. Returns when `host_hits` is complete. Not part of the reference API.
+void traverse_grid_to_host(const Grid& grid, const Tri* tris, const Ray* dev_rays, Hit* dev_hits, Hit* host_hits, int num_rays,
+                           bool prim_ids);
+
 /// Camera of a frame: what gen_camera of the reference's front end produces (src/main.cpp:18-23,42-50).
 struct FrameCamera { vec3 eye, right, up, dir; };
 
@@ -52,9 +58,16 @@ void generate_rays(const FrameCamera& cam, float clip, int width, int height, Ra
 /// hit point + `offset` x unit normal facing the ray, direction from a counter-based generator keyed by
 /// (`seed`, i), tmin 0, tmax `tmax`; rays that missed are emitted again unchanged. `out` may be `rays`.
 /// IEEE arithmetic only: oracle/hagrid_oracle.c og_bounce_rays produces the same bits on the CPU.
+/// `keys` (device, one int per ray, may be null = the ray's index in this buffer) names each ray's random stream: a
+/// shard of a frame passes the rays' indices in the whole frame and gets the rays the unsharded frame would get.
 /// Asynchronous on the legacy default stream. Not part of the reference API.
 void generate_bounce_rays(const Tri* tris, int num_tris, const Ray* rays, const Hit* hits, int num_rays,
-                          float offset, float tmax, unsigned seed, Ray* out);
+                          float offset, float tmax, unsigned seed, Ray* out, const int* keys = nullptr);
+
+/// Per-frame counters of a hit buffer (primitive-id hits): counters[0] += hits with id >= 0, counters[1] += sum of
+/// (id + 1); `counters` is device memory the caller zeroes. What the ranks of a sharded frame all-reduce.
+/// Asynchronous on the legacy default stream. Not part of the reference API.
+void count_hits(const Hit* hits, int num_hits, unsigned long long* counters);
 
 /// One frame of the reference's viewer (src/main.cpp:591-625) fused into one launch: primary rays are
 /// generated, traced and coloured on the device; `pixels` (device, width * height BGRA words) receives

@@ -165,6 +165,23 @@ HGB_API int  hgb_render_frame(hgb_scene* scene, const float cam[12], float clip,
  * bits on the CPU. The reference build of this ABI reports an error. */
 HGB_API int  hgb_generate_bounce_rays(hgb_scene* scene, const void* dev_rays, const void* dev_hits, int num_rays,
                                       float offset, float tmax, unsigned seed, void* dev_out);
+/* Same, for a shard of a frame: `dev_keys` (device, one int32 per ray, NULL = the ray's index in this buffer) names each
+ * ray's random stream. A rank that passes the indices its rays have in the whole frame gets exactly the second-wave
+ * rays the unsharded frame would get, so the gathered frame does not depend on the number of GPUs. */
+HGB_API int  hgb_generate_bounce_rays_keyed(hgb_scene* scene, const void* dev_rays, const void* dev_hits, int num_rays,
+                                            float offset, float tmax, unsigned seed, const void* dev_keys, void* dev_out);
+/* Per-frame counters of a buffer of primitive-id hits, the only thing the ranks of a sharded frame exchange
+ * (one all-reduce per frame): dev_counters[0] += hits with id >= 0, dev_counters[1] += sum of (id + 1);
+ * two uint64 in device memory, zeroed by the caller. Asynchronous on the legacy default stream. */
+HGB_API int  hgb_count_hits(hgb_scene* scene, const void* dev_hits, int num_hits, void* dev_counters);
+/* One two-wave frame (config C5) with HOST buffers: uploads `num_rays` primary rays, traces them, makes the bounce
+ * rays on the device from the resident rays and hits (hgb_generate_bounce_rays_keyed), traces those, and returns
+ * when both hit buffers (primitive ids) are complete in host memory. Upload, traversals and downloads overlap in
+ * chunks; the second wave never crosses PCIe as rays (the reference's front end would download the hits, generate on
+ * one CPU thread and upload 32 B per ray). The reference build of this ABI reports an error. */
+HGB_API int  hgb_trace_two_waves_host(hgb_scene* scene, const void* host_rays, int num_rays, const void* dev_keys,
+                                      float offset, float tmax, unsigned seed, void* host_hits_primary,
+                                      void* host_hits_bounce);
 
 /* Headless stand-in for the viewer's SDL window (src/main.cpp:558-625): a frame of BGRA words as written by
  * hgb_render_frame / update_surface goes to a binary PPM file (P6). */

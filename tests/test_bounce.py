@@ -202,3 +202,52 @@ def test_two_waves_on_the_device_equal_the_host_procedure(lib, ref_lib):
     with pytest.raises(HagridError):
         ref.bounce_rays(primary[:4], first[:4], 0.1, 1.0, 1)
     ref.close(); sc.close()
+
+
+@pytest.mark.gpu
+def test_a_sharded_frame_gets_the_second_wave_of_the_whole_frame(lib):
+    """hgb_generate_bounce_rays_keyed: a rank that passes its rays' indices in the whole frame as keys gets exactly the
+    rows of the unsharded second wave (SURVEY.md 8e: the gathered frame must not depend on the number of GPUs);
+    hgb_count_hits gives the counters the ranks all-reduce; hgb_trace_two_waves_host equals the device procedure."""
+    import torch
+    from hagrid_b200 import sharding
+    tris = scenes.atrium(60000, seed=5)
+    sc = Scene(tris, lib=lib)
+    sc.build_all(0.15, 3.0)
+    sc.setup_traversal()
+    lo, hi = scenes.scene_bbox(tris)
+    diag = float(np.linalg.norm(hi - lo))
+    W, H = 640, 360
+    primary = scenes.default_view(tris, W, H)
+    first = sc.trace(primary, HIT_PRIM_ID)
+    whole = sc.bounce_rays(primary, first, 1e-3 * diag, diag, 5)
+    second = sc.trace(whole, HIT_PRIM_ID)
+    world = 3
+    for rank in range(world):
+        idx = sharding.interleaved_bands(len(primary), rank, world, sharding.raster_granule(W))
+        mine = np.ascontiguousarray(primary[idx]); n = len(mine)
+        d_rays = torch.from_numpy(mine.view(np.float32).reshape(n, 8)).cuda()
+        d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+        d_out = torch.empty_like(d_rays)
+        d_keys = torch.from_numpy(idx.astype(np.int32)).cuda()
+        counters = torch.zeros(2, dtype=torch.int64, device="cuda")
+        sc.traverse(d_rays, d_hits, n, HIT_PRIM_ID)
+        sc.count_hits(d_hits, n, counters)
+        sc.bounce_rays_keyed(d_rays, d_hits, n, 1e-3 * diag, diag, 5, d_keys, d_out)
+        got = d_out.cpu().numpy().view(RAY_DTYPE).reshape(-1)
+        assert got.tobytes() == np.ascontiguousarray(whole[idx]).tobytes(), rank
+        ids = first["id"][idx]
+        assert [int(v) for v in counters.cpu()] == [int((ids >= 0).sum()), int((ids.astype(np.int64) + 1).sum())]
+        # the host-buffer frame of this shard
+        h_rays = torch.from_numpy(mine.view(np.float32).reshape(n, 8)).pin_memory()
+        h1 = torch.empty((n, 4), dtype=torch.float32).pin_memory(); h2 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        sc.trace_two_waves_host(h_rays, n, d_keys, 1e-3 * diag, diag, 5, h1, h2)
+        assert h1.numpy().view(HIT_DTYPE).reshape(-1).tobytes() == np.ascontiguousarray(first[idx]).tobytes()
+        assert h2.numpy().view(HIT_DTYPE).reshape(-1).tobytes() == np.ascontiguousarray(second[idx]).tobytes()
+    # without keys the stream is the ray's index in the buffer
+    d_rays = torch.from_numpy(primary.view(np.float32).reshape(-1, 8)).cuda()
+    d_hits = torch.from_numpy(first.view(np.float32).reshape(-1, 4)).cuda()
+    d_out = torch.empty_like(d_rays)
+    sc.bounce_rays_keyed(d_rays, d_hits, len(primary), 1e-3 * diag, diag, 5, None, d_out)
+    assert d_out.cpu().numpy().view(RAY_DTYPE).reshape(-1).tobytes() == whole.tobytes()
+    sc.close()

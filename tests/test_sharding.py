@@ -87,6 +87,65 @@ def test_two_rank_sharded_trace_equals_single_process(tmp_path):
         assert total[2] == 2.0          # max over ranks of the per-rank device time
 
 
+def _frame_worker(rank, world, port, out_dir):
+    """One rank of the sharded two-wave frame of bench.py --gpus N, with the CPU oracle standing in for the GPU:
+    bands dealt round-robin, second wave keyed by the rays' indices in the whole frame, one all-reduce of the counters."""
+    import torch
+    import torch.distributed as dist
+    from hagrid_b200 import scenes
+    from oracle import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tris, primary, grid, offset, tmax = _small_frame(oracle, scenes)
+    idx = sharding.interleaved_bands(primary.shape[0], rank, world, sharding.raster_granule(64))
+    mine = np.ascontiguousarray(primary[idx])
+    first = grid.traverse(tris, mine, mode=1)
+    # keyed generation = the rows of the generator run over the whole frame with these hits in place
+    everything = np.zeros(primary.shape[0], dtype=first.dtype); everything["id"] = -1
+    everything[idx] = first
+    bounce = np.ascontiguousarray(oracle.bounce_rays(tris, primary, everything, offset, tmax, 11)[idx])
+    second = grid.traverse(tris, bounce, mode=1)
+    counters = torch.tensor([int((first["id"] >= 0).sum() + (second["id"] >= 0).sum()),
+                             int((first["id"].astype(np.int64) + 1).sum() + (second["id"].astype(np.int64) + 1).sum())])
+    dist.all_reduce(counters)
+    np.save(os.path.join(out_dir, f"first_{rank}.npy"), first); np.save(os.path.join(out_dir, f"second_{rank}.npy"), second)
+    np.save(os.path.join(out_dir, f"idx_{rank}.npy"), idx); np.save(os.path.join(out_dir, f"counters_{rank}.npy"), counters.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _small_frame(oracle, scenes):
+    tris = scenes.small_mixed(3000, seed=9)
+    grid = oracle.Grid.build(tris, 0.15, 3.0)
+    grid.merge(0.995); grid.flatten(); grid.expand(3)
+    lo, hi = scenes.scene_bbox(tris)
+    diag = float(np.linalg.norm(hi - lo))
+    primary = scenes.primary_rays(lo - (hi - lo) * 0.5, 0.5 * (lo + hi), (0, 1, 0), 50.0, 64, 32, 4 * diag)
+    return tris, primary, grid, 1e-3 * diag, diag
+
+
+def test_two_rank_sharded_two_wave_frame_equals_the_unsharded_frame(tmp_path):
+    import torch.multiprocessing as mp
+    from hagrid_b200 import scenes
+    from oracle import oracle
+    world = 2
+    mp.spawn(_frame_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    tris, primary, grid, offset, tmax = _small_frame(oracle, scenes)
+    first = grid.traverse(tris, primary, mode=1)
+    second = grid.traverse(tris, oracle.bounce_rays(tris, primary, first, offset, tmax, 11), mode=1)
+    got1, got2 = np.empty_like(first), np.empty_like(second)
+    for r in range(world):
+        idx = np.load(tmp_path / f"idx_{r}.npy")
+        got1[idx] = np.load(tmp_path / f"first_{r}.npy"); got2[idx] = np.load(tmp_path / f"second_{r}.npy")
+    assert got1.tobytes() == first.tobytes() and got2.tobytes() == second.tobytes()
+    assert (first["id"] >= 0).sum() > 100
+    for r in range(world):
+        c = np.load(tmp_path / f"counters_{r}.npy")
+        assert c[0] == (first["id"] >= 0).sum() + (second["id"] >= 0).sum()
+        assert c[1] == (first["id"].astype(np.int64) + 1).sum() + (second["id"].astype(np.int64) + 1).sum()
+
+
 def test_reduce_counters_without_process_group_is_identity():
     local = np.array([3.0, 10.0, 0.5])
     assert np.array_equal(sharding.reduce_counters(local, None), local)
