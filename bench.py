@@ -248,11 +248,8 @@ def two_wave_frames(ctx: Ctx, lib, scene, tris, primary, reference, steps, warmu
 
         def step():
             counters.zero_()
-            scene.traverse(d_rays, d_hits1, n, HIT_PRIM_ID)
-            scene.count_hits(d_hits1, n, counters)
-            scene.bounce_rays_keyed(d_rays, d_hits1, n, offset, tmax, BOUNCE_SEED, d_keys, d_bounce)
-            scene.traverse(d_bounce, d_hits2, n, HIT_PRIM_ID)
-            scene.count_hits(d_hits2, n, counters)
+            # primary trace, hit count, bounce rays, second trace, hit count: one call, chunked over two streams
+            scene.trace_two_waves(d_rays, n, d_keys, offset, tmax, BOUNCE_SEED, d_hits1, d_bounce, d_hits2, counters)
             if world > 1 and collective:
                 dist.all_reduce(counters)               # the frame's only collective: 16 bytes
 

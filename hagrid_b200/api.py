@@ -85,6 +85,8 @@ _SIGNATURES = {
     "hgb_generate_bounce_rays_keyed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_uint,
                                                 C.c_void_p, C.c_void_p]),
     "hgb_count_hits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "hgb_trace_two_waves": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_uint,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hgb_trace_two_waves_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_uint,
                                           C.c_void_p, C.c_void_p]),
     "hgb_save_image": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
@@ -328,6 +330,13 @@ class Scene:
     def count_hits(self, dev_hits, num_hits: int, dev_counters):
         """dev_counters (two uint64, device) += [hits with id >= 0, sum of id + 1] (hgb_count_hits)."""
         self.lib.check(self.lib.dll.hgb_count_hits(self._h, _ptr(dev_hits), num_hits, _ptr(dev_counters)), "count_hits")
+
+    def trace_two_waves(self, dev_rays, num_rays: int, dev_keys, offset: float, tmax: float, seed: int, dev_hits_primary,
+                        dev_bounce_rays, dev_hits_bounce, dev_counters=None):
+        """One two-wave frame, everything resident (hgb_trace_two_waves)."""
+        self.lib.check(self.lib.dll.hgb_trace_two_waves(self._h, _ptr(dev_rays), num_rays, _ptr(dev_keys), offset, tmax,
+                                                        seed & 0xFFFFFFFF, _ptr(dev_hits_primary), _ptr(dev_bounce_rays),
+                                                        _ptr(dev_hits_bounce), _ptr(dev_counters)), "trace_two_waves")
 
     def trace_two_waves_host(self, host_rays, num_rays: int, dev_keys, offset: float, tmax: float, seed: int, host_hits_primary,
                              host_hits_bounce):

@@ -47,6 +47,9 @@ void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays,
                         Ray* dev_rays, Hit* dev_hits, bool prim_ids);
 void traverse_grid_to_host(const Grid& grid, const Tri* tris, const Ray* dev_rays, Hit* dev_hits, Hit* host_hits, int num_rays,
                            bool prim_ids);
+void trace_two_waves(const Grid& grid, const Tri* tris, int num_tris, const Ray* rays, int num_rays, const int* keys,
+                     float offset, float tmax, unsigned seed, Hit* hits_primary, Ray* bounce, Hit* hits_bounce,
+                     unsigned long long* counters);
 bool set_traversal_option(const char* key, int value);
 unsigned long long kernel_launch_count();
 void trim_device_pool();
@@ -462,6 +465,24 @@ int hgb_count_hits(hgb_scene* s, const void* dev_hits, int num_hits, void* dev_c
     return fail("count_hits: not part of the reference");
 #else
     count_hits(static_cast<const Hit*>(dev_hits), num_hits, static_cast<unsigned long long*>(dev_counters));
+    return 0;
+#endif
+}
+
+int hgb_trace_two_waves(hgb_scene* s, const void* dev_rays, int num_rays, const void* dev_keys, float offset, float tmax,
+                        unsigned seed, void* dev_hits_primary, void* dev_bounce_rays, void* dev_hits_bounce, void* dev_counters) {
+    if (!bind(s)) return -1;
+    if (!s->grid.entries) return fail("trace_two_waves: no grid");
+    if (!setup_matches(s)) return fail("trace_two_waves: hgb_setup_traversal was not called for this grid");
+    if (num_rays < 0 || (num_rays > 0 && (!dev_rays || !dev_hits_primary || !dev_bounce_rays || !dev_hits_bounce)))
+        return fail("trace_two_waves: bad argument");
+#ifdef HGB_REFERENCE_BUILD
+    (void)dev_keys; (void)offset; (void)tmax; (void)seed; (void)dev_counters;
+    return fail("trace_two_waves: the reference has no second-wave ray generation");
+#else
+    trace_two_waves(s->grid, s->tris, s->num_tris, static_cast<const Ray*>(dev_rays), num_rays, static_cast<const int*>(dev_keys),
+                    offset, tmax, seed, static_cast<Hit*>(dev_hits_primary), static_cast<Ray*>(dev_bounce_rays),
+                    static_cast<Hit*>(dev_hits_bounce), static_cast<unsigned long long*>(dev_counters));
     return 0;
 #endif
 }

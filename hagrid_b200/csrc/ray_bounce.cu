@@ -30,7 +30,7 @@ constexpr int kDiskTries = 8;
 
 __global__ void __launch_bounds__(256)
 bounce_rays(const Tri* __restrict__ tris, int num_tris, const Ray* rays, const Hit* __restrict__ hits, int num_rays,
-            float offset, float tmax, uint32_t seed, const int* __restrict__ keys, Ray* out) {
+            float offset, float tmax, uint32_t seed, const int* __restrict__ keys, int first_key, Ray* out) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= num_rays) return;
     const float4 a = reinterpret_cast<const float4*>(rays + i)[0];     // org, tmin
@@ -59,7 +59,7 @@ bounce_rays(const Tri* __restrict__ tris, int num_tris, const Ray* rays, const H
     // uniform point of the unit disk by rejection, lifted to the hemisphere: cosine-weighted direction
     // the random stream belongs to the ray, not to its place in this buffer: a shard of a frame passes the rays' indices
     // in the whole frame as keys and gets the rays the unsharded frame would get
-    const uint32_t base = mix32(seed ^ mix32(uint32_t(keys ? __ldg(keys + i) : i)));
+    const uint32_t base = mix32(seed ^ mix32(uint32_t(keys ? __ldg(keys + i) : first_key + i)));
     float dx = 0.0f, dy = 0.0f, s = 0.0f;
     for (int k = 0; k < kDiskTries; k++) {
         const float x = __fsub_rn(__fmul_rn(2.0f, draw(base, 2 * k)), 1.0f);
@@ -110,21 +110,28 @@ count_hits_kernel(const Hit* __restrict__ hits, int num_hits, unsigned long long
 
 } // namespace
 
-void generate_bounce_rays(const Tri* tris, int num_tris, const Ray* rays, const Hit* hits, int num_rays,
-                          float offset, float tmax, unsigned seed, Ray* out, const int* keys) {
+void generate_bounce_rays_on(cudaStream_t stream, const Tri* tris, int num_tris, const Ray* rays, const Hit* hits, int num_rays,
+                             float offset, float tmax, unsigned seed, Ray* out, const int* keys, int first_key) {
     if (num_rays <= 0) return;
-    bounce_rays<<<(num_rays + 255) / 256, 256>>>(tris, num_tris, rays, hits, num_rays, offset, tmax, seed, keys, out); count_launch();
+    bounce_rays<<<(num_rays + 255) / 256, 256, 0, stream>>>(tris, num_tris, rays, hits, num_rays, offset, tmax, seed, keys, first_key, out); count_launch();
     HGB_CUDA(cudaGetLastError());
 }
 
-void count_hits(const Hit* hits, int num_hits, unsigned long long* counters) {
+void count_hits_on(cudaStream_t stream, const Hit* hits, int num_hits, unsigned long long* counters) {
     if (num_hits <= 0) return;
     int sms = 0, dev = 0;
     HGB_CUDA(cudaGetDevice(&dev));
     HGB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int blocks = std::min((num_hits + 255) / 256, sms * 8);
-    count_hits_kernel<<<blocks, 256>>>(hits, num_hits, counters); count_launch();
+    count_hits_kernel<<<blocks, 256, 0, stream>>>(hits, num_hits, counters); count_launch();
     HGB_CUDA(cudaGetLastError());
 }
+
+void generate_bounce_rays(const Tri* tris, int num_tris, const Ray* rays, const Hit* hits, int num_rays,
+                          float offset, float tmax, unsigned seed, Ray* out, const int* keys) {
+    generate_bounce_rays_on(0, tris, num_tris, rays, hits, num_rays, offset, tmax, seed, out, keys, 0);
+}
+
+void count_hits(const Hit* hits, int num_hits, unsigned long long* counters) { count_hits_on(0, hits, num_hits, counters); }
 
 } // namespace hagrid

@@ -797,6 +797,8 @@ std::atomic<int> g_variant{-1};
 
 // Host-buffer frames: rays per full-size chunk (tuned on B200/PCIe 5, profiles/r02_e2e.md: 256 K rays = 8.6 MB up, 4.3 MB down)
 std::atomic<int> g_host_frame_chunk{256 * 1024};
+// trace_two_waves: chunks a frame is cut into (their chains alternate between two streams)
+std::atomic<int> g_two_wave_chunks{1};
 // rasters smaller than this many rays are traced one thread per ray (re-tiled): a small launch does not fill the resident warps
 std::atomic<int> g_tile_min_rays{1280 << 10};      // profiles/r02_traverse_experiments.md: half a 1920x1080 frame is on the line
 
@@ -837,6 +839,57 @@ void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* r
     }
 }
 
+/// What kind of buffer is this? A new one (other address or size) is looked at on the device before its first
+/// launch (a wait of about 10 us, once per buffer, instead of tracing its first frame with a kernel that may be the
+/// wrong one by a factor of 1.7); the answer is remembered on the host. A buffer known as a raster is not looked at
+/// again — the tile kernel reports when its contents stop behaving like one (feedback words) — and a buffer known
+/// as incoherent is looked at before every launch (a 10 us kernel in front of one that takes several hundred):
+/// callers reuse ray buffers. Work is enqueued on the legacy default stream. Returns the buffer's cache entry.
+DeviceState::SeenBuffer* classify_buffer(DeviceState& st, const Ray* rays, int num_rays) {
+    DeviceState::SeenBuffer* buf = nullptr;
+    st.launches++;
+    for (auto& e : st.seen)
+        if (e.rays == rays && e.count == num_rays) buf = &e;
+    const bool same = buf != nullptr;
+    if (!same) {
+        buf = &st.seen[0];
+        for (auto& e : st.seen)
+            if (e.used < buf->used) buf = &e;
+        buf->cls = -1; buf->feedback_armed = false;
+    }
+    buf->used = st.launches;
+    volatile int* answer = buf->host;
+    volatile int* fb = buf->host + 2;
+    if (!same) ;                                                          // nothing known yet
+    else if (buf->cls < 0 && *answer >= 0) buf->cls = *answer;            // the first look has finished
+    else if (buf->cls == 0 && *answer > 0) buf->cls = *answer;            // the latest look found a raster again
+    else if (buf->cls > 0 && buf->feedback_armed) {
+        // the launches reported since the last look
+        const int now_mixed = fb[0], now_launches = fb[1];
+        const int mixed = now_mixed - buf->feedback_mixed, launches = now_launches - buf->feedback_launches;
+        buf->feedback_mixed = now_mixed; buf->feedback_launches = now_launches;
+        const int tiles = (num_rays + 31) / 32;
+        if (launches > 0 && (long long)mixed * 4 > (long long)launches * tiles) {     // most warps mixed: not camera rays any more
+            buf->cls = 0;
+            buf->feedback_armed = false;
+            *answer = 0;
+        }
+    }
+    if (!same || buf->cls == 0) {
+        *answer = -1;
+        int* host_alias = nullptr;
+        HGB_CUDA(cudaHostGetDevicePointer(&host_alias, buf->host, 0));
+        detect_raster<<<1, 256>>>(rays, num_rays, buf->layout, host_alias); count_launch();
+        if (!same) {
+            HGB_CUDA(cudaStreamSynchronize(0));
+            buf->cls = *answer;
+        }
+        buf->rays = rays;
+        buf->count = num_rays;
+    }
+    return buf;
+}
+
 template <typename CellT, bool kPrimId>
 void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
     if (num_rays <= 0) return;
@@ -846,53 +899,7 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
     int* feedback = nullptr;
     DeviceState::SeenBuffer* buf = nullptr;
     if (variant >= 2 && variant <= 4) {
-        // What kind of buffer is this? A new one (other address or size) is looked at on the device before its
-        // first launch; the answer is remembered on the host.
-        // A buffer known as a raster is not looked at again — the tile kernel reports when its contents stop
-        // behaving like one (feedback words) — and a buffer known as incoherent is looked at before every
-        // launch (a 10 us kernel in front of one that takes several hundred): callers reuse ray buffers.
-        st.launches++;
-        for (auto& e : st.seen)
-            if (e.rays == rays && e.count == num_rays) buf = &e;
-        const bool same = buf != nullptr;
-        if (!same) {
-            buf = &st.seen[0];
-            for (auto& e : st.seen)
-                if (e.used < buf->used) buf = &e;
-            buf->cls = -1; buf->feedback_armed = false;
-        }
-        buf->used = st.launches;
-        volatile int* answer = buf->host;
-        volatile int* fb = buf->host + 2;
-        if (!same) ;                                                          // nothing known yet
-        else if (buf->cls < 0 && *answer >= 0) buf->cls = *answer;            // the first look has finished
-        else if (buf->cls == 0 && *answer > 0) buf->cls = *answer;            // the latest look found a raster again
-        else if (buf->cls > 0 && buf->feedback_armed) {
-            // the launches reported since the last look
-            const int now_mixed = fb[0], now_launches = fb[1];
-            const int mixed = now_mixed - buf->feedback_mixed, launches = now_launches - buf->feedback_launches;
-            buf->feedback_mixed = now_mixed; buf->feedback_launches = now_launches;
-            const int tiles = (num_rays + 31) / 32;
-            if (launches > 0 && (long long)mixed * 4 > (long long)launches * tiles) {     // most warps mixed: not camera rays any more
-                buf->cls = 0;
-                buf->feedback_armed = false;
-                *answer = 0;
-            }
-        }
-        if (!same || buf->cls == 0) {
-            *answer = -1;
-            int* host_alias = nullptr;
-            HGB_CUDA(cudaHostGetDevicePointer(&host_alias, buf->host, 0));
-            detect_raster<<<1, 256>>>(rays, num_rays, buf->layout, host_alias); count_launch();
-            if (!same) {
-                // a buffer never seen before: wait for the answer (about 10 us, once per buffer) instead of
-                // tracing its first frame with a kernel that may be the wrong one by a factor of 1.7
-                HGB_CUDA(cudaStreamSynchronize(0));
-                buf->cls = *answer;
-            }
-            buf->rays = rays;
-            buf->count = num_rays;
-        }
+        buf = classify_buffer(st, rays, num_rays);
         if (variant == 3) {
             // small buffers do not fill the resident-warp kernels (7 104 warps on 148 SMs): one thread per ray then
             if (buf->cls == 0) variant = num_rays < (128 << 10) ? 0 : 1;
@@ -1053,25 +1060,81 @@ void launch_to_host(const Grid& grid, const CellT* cells, const Tri* tris, const
     std::lock_guard<std::mutex> guard(st.lock);
     prepare_streams(st);
     cudaStream_t down = st.streams[1];
-    HGB_CUDA(cudaEventRecord(st.frame_start, 0));
-    HGB_CUDA(cudaStreamWaitEvent(down, st.frame_start, 0));
+    HGB_CUDA(cudaEventRecord(st.frame_start, 0));           // ordered after earlier default-stream work (the rays are made there)
+    for (int i = 1; i < DeviceState::kStreams; i++) HGB_CUDA(cudaStreamWaitEvent(st.streams[i], st.frame_start, 0));
+    // Chunks alternate between the two traversal streams: a launch over incoherent rays ends with a long tail of a few
+    // marching rays, and the next chunk's warps move in as the previous chunk's run dry
     constexpr int kChunks = 4;
     const long long step = ((long long)round_div(num_rays, kChunks) + kBlockThreads - 1) / kBlockThreads * kBlockThreads;
     int c = 0;
     for (long long begin = 0; begin < num_rays; begin += step, c++) {
         const int count = int(std::min<long long>(step, num_rays - begin));
+        cudaStream_t run = st.streams[2 + (c & 1)];
         // second-wave rays are incoherent by construction: no look at their layout
         int variant = traverse_variant();
         if (variant == 3) variant = count < (128 << 10) ? 0 : 1;
         else if (variant != 1) variant = 0;
         enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, dev_hits + begin, count, variant, nullptr, 0,
-                                st.vote_counter, st.tiles, st.num_sms, 0);
-        HGB_CUDA(cudaEventRecord(st.traced[c], 0));
+                                st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
+        HGB_CUDA(cudaEventRecord(st.traced[c], run));
         HGB_CUDA(cudaStreamWaitEvent(down, st.traced[c], 0));
         HGB_CUDA(cudaMemcpyAsync(host_hits + begin, dev_hits + begin, sizeof(Hit) * size_t(count), cudaMemcpyDeviceToHost, down));
     }
     HGB_CUDA(cudaGetLastError());
+    for (int i = 1; i < DeviceState::kStreams; i++) {
+        HGB_CUDA(cudaEventRecord(st.stream_done[i], st.streams[i]));
+        HGB_CUDA(cudaStreamWaitEvent(0, st.stream_done[i], 0));   // a timer on the default stream brackets the work
+    }
     HGB_CUDA(cudaStreamSynchronize(down));
+}
+
+/// One two-wave frame with everything resident (BASELINE config C5): trace, count, bounce rays, trace, count. The
+/// frame can be cut into chunks ("two_wave_chunks") whose chains alternate between two streams, the idea being that one
+/// chunk's work fills the tails of the other's launches; measured on the 7.8 M-triangle frame it loses (1.42 / 1.59 /
+/// 1.93 / 1.96 / 2.68 ms for 1 / 2 / 3 / 4 / 8 chunks: every chunk's launches bring their own tail and the smaller
+/// launches fall off the tile kernel), so a frame is one chain by default. Joined back into the legacy default stream.
+template <typename CellT>
+void launch_two_waves(const Grid& grid, const CellT* cells, const Tri* tris, int num_tris, const Ray* rays, int num_rays,
+                      const int* keys, float offset, float tmax, unsigned seed, Hit* hits_primary, Ray* bounce, Hit* hits_bounce,
+                      unsigned long long* counters) {
+    if (num_rays <= 0) return;
+    DeviceState& st = device_state();
+    std::lock_guard<std::mutex> guard(st.lock);
+    prepare_streams(st);
+    int forced = traverse_variant();
+    int width = 0;
+    if (forced >= 2 && forced <= 4) width = std::max(0, classify_buffer(st, rays, num_rays)->cls);
+    const int granule = width > 0 ? width * kTileH : kBlockThreads;
+    const int chunks = std::max(1, std::min(g_two_wave_chunks.load(), num_rays / (256 << 10)));
+    const long long step = ((long long)round_div(num_rays, chunks) + granule - 1) / granule * granule;
+    HGB_CUDA(cudaEventRecord(st.frame_start, 0));
+    for (int i = 2; i < DeviceState::kStreams; i++) HGB_CUDA(cudaStreamWaitEvent(st.streams[i], st.frame_start, 0));
+    int c = 0;
+    for (long long begin = 0; begin < num_rays; begin += step, c++) {
+        const int count = int(std::min<long long>(step, num_rays - begin));
+        cudaStream_t run = st.streams[2 + (c & 1)];
+        int first = forced, second = forced;
+        if (forced == 3) {
+            first = width > 0 ? (count < g_tile_min_rays.load() ? 2 : 4) : (count < (128 << 10) ? 0 : 1);
+            second = count < (128 << 10) ? 0 : 1;
+        } else if (forced == 2 || forced == 4) {
+            if (width <= 0) first = 0;
+            second = 0;
+        }
+        enqueue<CellT, true>(grid, cells, tris, rays + begin, hits_primary + begin, count, first, nullptr, width,
+                             st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
+        if (counters) count_hits_on(run, hits_primary + begin, count, counters);
+        generate_bounce_rays_on(run, tris, num_tris, rays + begin, hits_primary + begin, count, offset, tmax, seed, bounce + begin,
+                                keys ? keys + begin : nullptr, int(begin));
+        enqueue<CellT, true>(grid, cells, tris, bounce + begin, hits_bounce + begin, count, second, nullptr, 0,
+                             st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
+        if (counters) count_hits_on(run, hits_bounce + begin, count, counters);
+    }
+    HGB_CUDA(cudaGetLastError());
+    for (int i = 2; i < DeviceState::kStreams; i++) {
+        HGB_CUDA(cudaEventRecord(st.stream_done[i], st.streams[i]));
+        HGB_CUDA(cudaStreamWaitEvent(0, st.stream_done[i], 0));
+    }
 }
 
 template <bool kPrimId>
@@ -1150,6 +1213,7 @@ void render_frame(const Grid& grid, const Tri* tris, const FrameCamera& cam, flo
 bool set_traversal_option(const char* key, int value) {
     if (!std::strcmp(key, "traverse_variant")) { g_variant.store(value); return true; }
     if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk.store(value > 0 ? value : 256 * 1024); return true; }
+    if (!std::strcmp(key, "two_wave_chunks")) { g_two_wave_chunks.store(value > 0 ? min(value, 16) : 1); return true; }
     if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (1280 << 10)); return true; }
     return false;
 }
@@ -1160,6 +1224,15 @@ void traverse_grid(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits
 
 void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, Hit* hits, int num_rays) {
     dispatch<true>(grid, tris, rays, hits, num_rays);
+}
+
+void trace_two_waves(const Grid& grid, const Tri* tris, int num_tris, const Ray* rays, int num_rays, const int* keys,
+                     float offset, float tmax, unsigned seed, Hit* hits_primary, Ray* bounce, Hit* hits_bounce,
+                     unsigned long long* counters) {
+    if (grid.small_cells) launch_two_waves<SmallCell>(grid, grid.small_cells, tris, num_tris, rays, num_rays, keys, offset, tmax, seed,
+                                                      hits_primary, bounce, hits_bounce, counters);
+    else                  launch_two_waves<Cell>(grid, grid.cells, tris, num_tris, rays, num_rays, keys, offset, tmax, seed,
+                                                 hits_primary, bounce, hits_bounce, counters);
 }
 
 void traverse_grid_to_host(const Grid& grid, const Tri* tris, const Ray* dev_rays, Hit* dev_hits, Hit* host_hits, int num_rays,

@@ -37,6 +37,15 @@ void traverse_grid_prim_ids(const Grid& grid, const Tri* tris, const Ray* rays, 
 void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays, Hit* host_hits, int num_rays,
                         Ray* dev_rays, Hit* dev_hits, bool prim_ids);
 
+/// One two-wave frame (BASELINE config C5) with everything resident, in one call: primary rays -> `hits_primary`
+/// (primitive ids), their bounce rays (generate_bounce_rays with `keys`) -> `bounce`, those traced -> `hits_bounce`;
+/// `counters` (two uint64, device, zeroed by the caller, may be null) receives count_hits of both hit buffers.
+/// Ordered after earlier work on the legacy default stream and joined back into it. Same results as the five separate
+/// calls. Not part of the reference API.
+void trace_two_waves(const Grid& grid, const Tri* tris, int num_tris, const Ray* rays, int num_rays, const int* keys,
+                     float offset, float tmax, unsigned seed, Hit* hits_primary, Ray* bounce, Hit* hits_bounce,
+                     unsigned long long* counters);
+
 /// Device-resident rays whose hits are wanted in host memory (the second wave of a frame: its rays were made on the
 /// device by generate_bounce_rays): traced in chunks, every chunk's hits travel to the host while the next chunk is
 /// traced. Returns when `host_hits` is complete. Not part of the reference API.

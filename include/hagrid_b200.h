@@ -174,6 +174,14 @@ HGB_API int  hgb_generate_bounce_rays_keyed(hgb_scene* scene, const void* dev_ra
  * (one all-reduce per frame): dev_counters[0] += hits with id >= 0, dev_counters[1] += sum of (id + 1);
  * two uint64 in device memory, zeroed by the caller. Asynchronous on the legacy default stream. */
 HGB_API int  hgb_count_hits(hgb_scene* scene, const void* dev_hits, int num_hits, void* dev_counters);
+/* One two-wave frame (config C5) with everything resident in HBM, in one call: primary rays -> dev_hits_primary
+ * (primitive ids), their bounce rays (hgb_generate_bounce_rays_keyed) -> dev_bounce_rays, those traced ->
+ * dev_hits_bounce; dev_counters (two uint64, zeroed by the caller, may be NULL) receives hgb_count_hits of both hit
+ * buffers. Same results as the five separate calls. Ordered after earlier work on the legacy default stream and
+ * joined back into it; asynchronous. The reference build of this ABI reports an error. */
+HGB_API int  hgb_trace_two_waves(hgb_scene* scene, const void* dev_rays, int num_rays, const void* dev_keys,
+                                 float offset, float tmax, unsigned seed, void* dev_hits_primary,
+                                 void* dev_bounce_rays, void* dev_hits_bounce, void* dev_counters);
 /* One two-wave frame (config C5) with HOST buffers: uploads `num_rays` primary rays, traces them, makes the bounce
  * rays on the device from the resident rays and hits (hgb_generate_bounce_rays_keyed), traces those, and returns
  * when both hit buffers (primitive ids) are complete in host memory. Upload, traversals and downloads overlap in

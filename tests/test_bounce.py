@@ -238,6 +238,16 @@ def test_a_sharded_frame_gets_the_second_wave_of_the_whole_frame(lib):
         assert got.tobytes() == np.ascontiguousarray(whole[idx]).tobytes(), rank
         ids = first["id"][idx]
         assert [int(v) for v in counters.cpu()] == [int((ids >= 0).sum()), int((ids.astype(np.int64) + 1).sum())]
+        # the whole frame of this shard in one call (chunk chains on two streams): same buffers, same counters
+        one_hits1, one_hits2, one_bounce = torch.zeros_like(d_hits), torch.zeros_like(d_hits), torch.zeros_like(d_rays)
+        one_counters = torch.zeros(2, dtype=torch.int64, device="cuda")
+        sc.trace_two_waves(d_rays, n, d_keys, 1e-3 * diag, diag, 5, one_hits1, one_bounce, one_hits2, one_counters)
+        assert one_hits1.cpu().numpy().view(HIT_DTYPE).reshape(-1).tobytes() == np.ascontiguousarray(first[idx]).tobytes()
+        assert one_bounce.cpu().numpy().view(RAY_DTYPE).reshape(-1).tobytes() == np.ascontiguousarray(whole[idx]).tobytes()
+        assert one_hits2.cpu().numpy().view(HIT_DTYPE).reshape(-1).tobytes() == np.ascontiguousarray(second[idx]).tobytes()
+        ids2 = second["id"][idx]
+        assert [int(v) for v in one_counters.cpu()] == [int((ids >= 0).sum() + (ids2 >= 0).sum()),
+                                                       int((ids.astype(np.int64) + 1).sum() + (ids2.astype(np.int64) + 1).sum())]
         # the host-buffer frame of this shard
         h_rays = torch.from_numpy(mine.view(np.float32).reshape(n, 8)).pin_memory()
         h1 = torch.empty((n, 4), dtype=torch.float32).pin_memory(); h2 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
