@@ -89,6 +89,10 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hgb_trace_two_waves_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_uint,
                                           C.c_void_p, C.c_void_p]),
+    "hgb_prim_exclusive_scan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "hgb_prim_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "hgb_prim_partition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "hgb_prim_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "hgb_save_image": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "hgb_rays_file_count": (C.c_longlong, [C.c_char_p]),
     "hgb_load_rays": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_float, C.c_float, C.c_void_p]),

@@ -50,6 +50,10 @@ void traverse_grid_to_host(const Grid& grid, const Tri* tris, const Ray* dev_ray
 void trace_two_waves(const Grid& grid, const Tri* tris, int num_tris, const Ray* rays, int num_rays, const int* keys,
                      float offset, float tmax, unsigned seed, Hit* hits_primary, Ray* bounce, Hit* hits_bounce,
                      unsigned long long* counters);
+void prim_exclusive_scan(MemManager& mem, const void* in, int n, int elem_bytes, void* out);
+void prim_reduce(MemManager& mem, const void* in, int n, int op, void* out);
+int prim_partition(MemManager& mem, const int* in, const int* flags, int n, int* out);
+void prim_sort_pairs(MemManager& mem, int* keys, int* vals, int n, int bits);
 bool set_traversal_option(const char* key, int value);
 unsigned long long kernel_launch_count();
 void trim_device_pool();
@@ -717,6 +721,40 @@ int hgb_copy_to_host(hgb_scene* s, void* host_dst, const void* dev_src, size_t b
     if (bytes) s->mem.copy<Copy::DEV_TO_HST>(static_cast<char*>(host_dst), static_cast<const char*>(dev_src), bytes);
     return 0;
 }
+
+#ifdef HGB_REFERENCE_BUILD
+int hgb_prim_exclusive_scan(hgb_scene*, const void*, int, int, void*) { return fail("prim: the reference build wraps CUB (src/parallel.cuh), nothing of its own to call"); }
+int hgb_prim_reduce(hgb_scene*, const void*, int, int, void*) { return fail("prim: not part of the reference build"); }
+int hgb_prim_partition(hgb_scene*, const void*, const void*, int, void*) { return fail("prim: not part of the reference build"); }
+int hgb_prim_sort_pairs(hgb_scene*, void*, void*, int, int) { return fail("prim: not part of the reference build"); }
+#else
+int hgb_prim_exclusive_scan(hgb_scene* s, const void* dev_in, int n, int elem_bytes, void* dev_out) {
+    if (!bind(s)) return -1;
+    if (n < 0 || !dev_out || (n > 0 && !dev_in) || (elem_bytes != 4 && elem_bytes != 8)) return fail("prim_exclusive_scan: bad argument");
+    prim_exclusive_scan(s->mem, dev_in, n, elem_bytes, dev_out);
+    return 0;
+}
+
+int hgb_prim_reduce(hgb_scene* s, const void* dev_in, int n, int op, void* dev_out) {
+    if (!bind(s)) return -1;
+    if (n < 0 || !dev_out || (n > 0 && !dev_in) || op < 0 || op > 3) return fail("prim_reduce: bad argument");
+    prim_reduce(s->mem, dev_in, n, op, dev_out);
+    return 0;
+}
+
+int hgb_prim_partition(hgb_scene* s, const void* dev_in, const void* dev_flags, int n, void* dev_out) {
+    if (!bind(s)) return -1;
+    if (n < 0 || (n > 0 && (!dev_in || !dev_flags || !dev_out))) return fail("prim_partition: bad argument");
+    return prim_partition(s->mem, static_cast<const int*>(dev_in), static_cast<const int*>(dev_flags), n, static_cast<int*>(dev_out));
+}
+
+int hgb_prim_sort_pairs(hgb_scene* s, void* dev_keys, void* dev_vals, int n, int bits) {
+    if (!bind(s)) return -1;
+    if (n < 0 || bits < 0 || bits > 31 || (n > 0 && (!dev_keys || !dev_vals))) return fail("prim_sort_pairs: bad argument");
+    prim_sort_pairs(s->mem, static_cast<int*>(dev_keys), static_cast<int*>(dev_vals), n, bits);
+    return 0;
+}
+#endif
 
 unsigned long long hgb_kernel_launches(void) {
 #ifdef HGB_REFERENCE_BUILD

@@ -480,7 +480,7 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
     int* counts = mem.alloc<int>(size_t(num_tris) + 1);
     int* refs_per_cell = mem.alloc<int>(num_top);
     int* log_dims = mem.alloc<int>(num_top);
-    int* scan_tmp = mem.alloc<int>(prim::num_tiles(num_tris) + 1);
+    int* scan_tmp = mem.alloc<int>(prim::scan_scratch_elems<int>(num_tris));
     mem.zero(refs_per_cell, num_top);
     mem.zero(totals, 8);
     count_refs<<<blocks_for(num_tris), kBlock>>>(P, tris, num_tris, counts, refs_per_cell); count_launch();
@@ -520,7 +520,7 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
         int* child_start = mem.alloc<int>(size_t(num_cells) + 1);
         int* codes = mem.alloc<int>(std::max(num_refs, 1));
         auto pos = mem.alloc<unsigned long long>(size_t(num_refs) + 1);
-        auto scan_tmp64 = mem.alloc<unsigned long long>(prim::num_tiles(std::max(num_refs, num_cells)) + 2);
+        auto scan_tmp64 = mem.alloc<unsigned long long>(prim::scan_scratch_elems<unsigned long long>(std::max(num_refs, num_cells)));
         auto totals64 = reinterpret_cast<unsigned long long*>(totals + 4);
 
         prim::exclusive_scan<int>(SplitToEight{split}, num_cells, child_start, reinterpret_cast<int*>(scan_tmp64), totals + 2);
@@ -585,7 +585,7 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
         mem.free(levels[i].entries);
     }
     int* leaf_index = mem.alloc<int>(size_t(total_cells) + 1);
-    int* leaf_tmp = mem.alloc<int>(prim::num_tiles(total_cells) + 1);
+    int* leaf_tmp = mem.alloc<int>(prim::scan_scratch_elems<int>(total_cells));
     prim::exclusive_scan<int>(IsLeaf{entries}, total_cells, leaf_index, leaf_tmp, totals + 0);
     int num_leaves = 0;
     HGB_CUDA(cudaMemcpy(&num_leaves, totals, sizeof(int), cudaMemcpyDeviceToHost));

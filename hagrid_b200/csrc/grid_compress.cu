@@ -66,8 +66,8 @@ bool compress_grid(MemManager& mem, Grid& grid) {
 
     const int num_cells = grid.num_cells;
     int* list_start = mem.alloc<int>(size_t(num_cells) + 1);
-    int* scan_tmp = mem.alloc<int>(prim::num_tiles(num_cells) + 2);
-    int* total_dev = scan_tmp + prim::num_tiles(num_cells) + 1;
+    int* scan_tmp = mem.alloc<int>(prim::scan_scratch_elems<int>(num_cells) + 1);
+    int* total_dev = scan_tmp + prim::scan_scratch_elems<int>(num_cells);
     SmallCell* small_cells = mem.alloc<SmallCell>(std::max(num_cells, 1));
     prim::exclusive_scan<int>(SentinelCount{grid.cells}, num_cells, list_start, scan_tmp, total_dev);
     int num_words = 0;

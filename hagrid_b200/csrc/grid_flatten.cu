@@ -119,8 +119,8 @@ void flatten_grid(MemManager& mem, Grid& grid) {
 
     // where each flattened node starts inside its group, and the size of every group
     int* node_start = mem.alloc<int>(size_t(grid.num_entries) + 1);
-    int* scan_tmp = mem.alloc<int>(prim::num_tiles(grid.num_entries) + 2);
-    int* total_dev = scan_tmp + prim::num_tiles(grid.num_entries) + 1;
+    int* scan_tmp = mem.alloc<int>(prim::scan_scratch_elems<int>(grid.num_entries) + 1);
+    int* total_dev = scan_tmp + prim::scan_scratch_elems<int>(grid.num_entries);
     std::vector<int> group_offset(std::max(grid.shift, 1), 0), group_words(std::max(grid.shift, 1), 0);
     int total_entries = grid.offsets[0];
     for (int level = 0; level < grid.shift; level += kFlatLevels) {

@@ -285,8 +285,8 @@ void merge_grid(MemManager& mem, Grid& grid, float alpha) {
     b.new_counts = mem.alloc<int>(n);
     b.new_cell_ids = mem.alloc<int>(n);
     b.scan = mem.alloc<unsigned long long>(n);
-    b.scan_tmp = mem.alloc<unsigned long long>(prim::num_tiles(grid.num_cells) + 3);
-    b.totals = b.scan_tmp + prim::num_tiles(grid.num_cells) + 1;       // two slots, used alternately
+    b.scan_tmp = mem.alloc<unsigned long long>(prim::scan_scratch_elems<unsigned long long>(grid.num_cells) + 2);
+    b.totals = b.scan_tmp + prim::scan_scratch_elems<unsigned long long>(grid.num_cells);       // two slots, used alternately
 
     const vec3 extents = grid.bbox.extents();
     const ivec3 dims = grid.dims << grid.shift;

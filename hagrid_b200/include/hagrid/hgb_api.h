@@ -109,5 +109,19 @@ void expand_grid(MemManager& mem, Grid& grid, const Tri* tris, int iters);
 /// when a virtual dimension does not fit 16 bits.
 bool compress_grid(MemManager& mem, Grid& grid);
 
+// ------------------------------------------------------------------ device-wide primitives
+// What the reference's `Parallel` wrapper offers on top of CUB (src/parallel.cuh:12-89), on this library's own kernels;
+// all pointers are device pointers, scratch comes from `mem`, work runs on the legacy default stream.
+/// out[i] = sum of in[0, i) for i in [0, n]; `out` has n + 1 elements and may be `in`. elem_bytes 4: int32; 8: two packed
+/// 32-bit counters per element (every prefix of each half below 2^32).
+void prim_exclusive_scan(MemManager& mem, const void* in, int n, int elem_bytes, void* out);
+/// *out = reduction of in[0, n): op 0 = sum of int32, 1 = max of int32, 2 = min of float, 3 = max of float (4 bytes).
+void prim_reduce(MemManager& mem, const void* in, int n, int op, void* out);
+/// cub::DevicePartition::Flagged's order: items with a non-zero flag first, in input order, the others behind them in
+/// REVERSE input order (the order the reference's build relies on, src/build.cu:568-569). Returns the number kept.
+int prim_partition(MemManager& mem, const int* in, const int* flags, int n, int* out);
+/// Stable sort of (key, value) pairs by the low `bits` bits of the non-negative keys, in place.
+void prim_sort_pairs(MemManager& mem, int* keys, int* vals, int n, int bits);
+
 } // namespace hagrid
 #endif

@@ -191,6 +191,22 @@ HGB_API int  hgb_trace_two_waves_host(hgb_scene* scene, const void* host_rays, i
                                       float offset, float tmax, unsigned seed, void* host_hits_primary,
                                       void* host_hits_bounce);
 
+/* Device-wide primitives on their own: what the reference's `Parallel` wrapper offers on top of CUB
+ * (src/parallel.cuh:12-89 -- scan :29-41, reduce :43-55, partition :57-71, sort_pairs :73-86), served by this library's
+ * hand-written kernels. The construction pipeline uses them fused with its own functors; these entry points make them
+ * testable and measurable in isolation (tests/test_primitives.py, tools/gpu_primitives_bench.py vs the toolkit's CUB).
+ * All pointers are device pointers; scratch comes from the scene's pool; the reference build reports an error.
+ *   hgb_prim_exclusive_scan  dev_out[i] = sum of dev_in[0, i), i in [0, n] (n + 1 outputs, may alias the input);
+ *                            elem_bytes 4 = int32, 8 = two packed 32-bit counters per element
+ *   hgb_prim_reduce          op 0 = sum of int32, 1 = max of int32, 2 = min of float, 3 = max of float -> 4 bytes
+ *   hgb_prim_partition       cub::DevicePartition::Flagged order: flagged items first in input order, the others behind
+ *                            them in REVERSE input order (src/build.cu:568-569 relies on it); returns the number kept
+ *   hgb_prim_sort_pairs      stable sort of int32 (key, value) pairs by the low `bits` bits of the keys, in place */
+HGB_API int  hgb_prim_exclusive_scan(hgb_scene* scene, const void* dev_in, int n, int elem_bytes, void* dev_out);
+HGB_API int  hgb_prim_reduce(hgb_scene* scene, const void* dev_in, int n, int op, void* dev_out);
+HGB_API int  hgb_prim_partition(hgb_scene* scene, const void* dev_in, const void* dev_flags, int n, void* dev_out);
+HGB_API int  hgb_prim_sort_pairs(hgb_scene* scene, void* dev_keys, void* dev_vals, int n, int bits);
+
 /* Headless stand-in for the viewer's SDL window (src/main.cpp:558-625): a frame of BGRA words as written by
  * hgb_render_frame / update_surface goes to a binary PPM file (P6). */
 HGB_API int  hgb_save_image(const char* path, const void* host_bgra, int width, int height);
