@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "device_math.cuh"
+#include "primitives.cuh"
 #include "runtime.h"
 #include "traverse.h"
 
@@ -616,7 +617,9 @@ traverse_voting(const __grid_constant__ TraversalParams P,
                 const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                 const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                 const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
-                int* __restrict__ next_ray) {
+                int* __restrict__ next_ray, const int* __restrict__ order) {
+    // `order` (may be null): the k-th ray handed out is rays[order[k]] (ray binning, see bin_rays); hits go to the
+    // ray's own slot, so the caller sees nothing of it
     constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
     constexpr unsigned kAll = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -646,8 +649,9 @@ traverse_voting(const __grid_constant__ TraversalParams P,
         if (idle == kAll && drained) break;
         if (!drained && __popc(idle) >= kVoteRefillMinLanes) {
             if (ray_id < 0) {
-                const int id = pool + __popc(idle & ((1u << lane) - 1u));
+                int id = pool + __popc(idle & ((1u << lane) - 1u));
                 if (id < pool_end) {
+                    if (order) id = __ldg(order + id);
                     if (start_ray(r, P, rays, id)) ray_id = id;
                     else finish_ray<kPrimId>(r, hits, id);
                 }
@@ -737,6 +741,8 @@ struct DeviceState {
     unsigned long long launches = 0;
     int* seen_host = nullptr;        // pinned block behind seen[].host
     int num_sms = 0;
+    int* sort_scratch = nullptr;     // ray binning ("ray_sort"): keys, order and the sort's scratch
+    size_t sort_capacity = 0;
     // host-buffer frames (traverse_grid_host): one upload stream, one download stream, two traversal streams
     static constexpr int kStreams = 4, kMaxChunks = 64;
     cudaStream_t streams[kStreams] = {};            // 0 = upload, 1 = download, 2 and 3 = traversal
@@ -812,13 +818,32 @@ int traverse_variant() {
     return v;
 }
 
+/// Ray binning for incoherent buffers (the north star's "warp-sorted ray packets"): key = direction octant (3 bits) above
+/// the top-level cell the ray enters the grid in; rays sorted by that key start their march in the same top-level
+/// cell, heading the same way. The sort is this library's own (primitives.cuh) and runs inside the traversal call.
+/// Measured on C3 and on the second wave of C5 (profiles/r02_traverse_experiments.md): off by default.
+__global__ void __launch_bounds__(256) ray_bin_keys(const __grid_constant__ TraversalParams P, const Ray* __restrict__ rays, int num_rays,
+                                                    int* __restrict__ keys, int* __restrict__ order) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= num_rays) return;
+    RayState r;
+    const bool ok = start_ray(r, P, rays, i);
+    const int top_z = P.dims_z >> P.shift;
+    int key = P.top_x * P.top_y * top_z * 8;               // rays that miss the grid: behind everything else
+    if (ok) key = octant_of(r) * (P.top_x * P.top_y * top_z) + (r.vx >> P.shift) + P.top_x * ((r.vy >> P.shift) + P.top_y * (r.vz >> P.shift));
+    keys[i] = key;
+    order[i] = i;
+}
+
+std::atomic<int> g_ray_sort{0};
+
 /// Enqueues one traversal launch on `stream`: 1 = persistent voting warps (needs `vote_counter`), 4 = resident
 /// warps pulling tiles (needs `ticket`), otherwise one thread per ray; 2 and 4 re-tile by the raster width in
 /// `layout[0]` (device) or `host_width`.
 template <typename CellT, bool kPrimId>
 void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays,
              int variant, const int* layout, int host_width, int* vote_counter, Ticket& ticket, int num_sms, cudaStream_t stream,
-             int* feedback = nullptr) {
+             int* feedback = nullptr, const int* order = nullptr) {
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
     const TraversalParams P = params_of(grid);
     if (variant == 4) {
@@ -832,7 +857,7 @@ void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* r
         // every warp reserves two blocks of rays up front: no more warps than there are blocks
         const int blocks = max(1, min(num_sms * kVoteBlocksPerSm, round_div(num_rays, 2 * kVoteBlock * (kBlockThreads / 32))));
         traverse_voting<CellT, kPrimId><<<blocks, kBlockThreads, 0, stream>>>(
-            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, vote_counter); count_launch();
+            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, vote_counter, order); count_launch();
     } else {
         traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128, 0, stream>>>(
             P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width); count_launch();
@@ -916,8 +941,25 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
         }
     }
     const bool tiled = variant == 2 || variant == 4;
+    const int* order = nullptr;
+    if (variant == 1 && g_ray_sort.load()) {
+        // experiment ("ray_sort"): bin the rays by (octant, entry cell) first; scratch is kept per device
+        const TraversalParams P = params_of(grid);
+        const size_t need = size_t(num_rays) * 4 + prim::sort_scratch_ints(num_rays);
+        if (need > st.sort_capacity) {
+            if (st.sort_scratch) HGB_CUDA(cudaFree(st.sort_scratch));
+            HGB_CUDA(cudaMalloc(&st.sort_scratch, need * sizeof(int)));
+            st.sort_capacity = need;
+        }
+        int* keys = st.sort_scratch; int* idx = keys + num_rays; int* keys_alt = idx + num_rays; int* idx_alt = keys_alt + num_rays;
+        ray_bin_keys<<<round_div(num_rays, 256), 256>>>(P, rays, num_rays, keys, idx); count_launch();
+        const int cells_top = P.top_x * P.top_y * (P.dims_z >> P.shift) * 8 + 1;
+        int bits = 1;
+        while ((1 << bits) < cells_top) bits++;
+        order = prim::sort_pairs(keys, idx, keys_alt, idx_alt, num_rays, bits, idx_alt + num_rays) ? idx_alt : idx;
+    }
     enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, tiled && buf ? buf->layout : nullptr, 0,
-                            st.vote_counter, st.tiles, st.num_sms, 0, feedback);
+                            st.vote_counter, st.tiles, st.num_sms, 0, feedback, order);
     if (feedback) {
         // copied back after launches 1, 2, 4 and then every 8th: one 8-byte copy in eight launches
         const int tick = ++buf->feedback_tick;
@@ -1213,6 +1255,7 @@ void render_frame(const Grid& grid, const Tri* tris, const FrameCamera& cam, flo
 bool set_traversal_option(const char* key, int value) {
     if (!std::strcmp(key, "traverse_variant")) { g_variant.store(value); return true; }
     if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk.store(value > 0 ? value : 256 * 1024); return true; }
+    if (!std::strcmp(key, "ray_sort")) { g_ray_sort.store(value != 0); return true; }
     if (!std::strcmp(key, "two_wave_chunks")) { g_two_wave_chunks.store(value > 0 ? min(value, 16) : 1); return true; }
     if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (1280 << 10)); return true; }
     return false;
