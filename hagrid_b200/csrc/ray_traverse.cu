@@ -92,7 +92,6 @@ struct RayState {
     int   hit_id;
     int   steps;
     int   vx, vy, vz;                   // current voxel
-    float tlast;                        // where the march stood when it was interrupted (march with a step budget)
 };
 
 /// Ray/triangle test, expression shapes as in the reference SASS:
@@ -332,17 +331,15 @@ __device__ __forceinline__ bool left_grid(const RayState& r, const TraversalPara
     return (unsigned(r.vx) >= unsigned(P.dims_x)) | (unsigned(r.vy) >= unsigned(P.dims_y)) | (unsigned(r.vz) >= unsigned(P.dims_z));
 }
 
-/// The march of one ray through the grid after init_ray (src/traverse.cu:56-90). kBudget: the march is interrupted
-/// (returns false, r.tlast = where it stands) once the ray has taken `limit` steps; somebody else finishes it.
-template <typename CellT, int kOct = -1, bool kBudget = false>
-__device__ __forceinline__ bool walk(RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
+/// The march of one ray through the grid after init_ray (src/traverse.cu:56-90)
+template <typename CellT, int kOct = -1>
+__device__ __forceinline__ void walk(RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
                                      const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
-                                     const Tri* __restrict__ tris, int limit = 0) {
+                                     const Tri* __restrict__ tris) {
     while (true) {
         const float texit = visit_cell<CellT, kOct>(r, P, entries, cells, ref_ids, tris);
-        if (r.hit_t <= texit) return true;
-        if (left_grid(r, P)) return true;
-        if (kBudget && r.steps >= limit) { r.tlast = texit; return false; }
+        if (r.hit_t <= texit) break;
+        if (left_grid(r, P)) break;
     }
 }
 
@@ -383,12 +380,11 @@ __device__ __forceinline__ int octant_of(const RayState& r) {
 
 /// March of the lanes with `ok` set. Called by all 32 lanes of a converged warp: when every marching lane has
 /// the same direction octant — the rule for an 8x4 tile of camera rays — the warp takes the loop specialised
-/// for it, otherwise the generic one. Same cells, same triangles, same order either way. kBudget: lanes whose ray
-/// is not finished after `limit` steps come back with `ok` still set.
-template <typename CellT, bool kBudget = false>
-__device__ __forceinline__ bool walk_warp(bool& ok, RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
+/// for it, otherwise the generic one. Same cells, same triangles, same order either way.
+template <typename CellT>
+__device__ __forceinline__ bool walk_warp(bool ok, RayState& r, const TraversalParams& P, const uint32_t* __restrict__ entries,
                                           const CellT* __restrict__ cells, const int* __restrict__ ref_ids,
-                                          const Tri* __restrict__ tris, int limit = 0) {
+                                          const Tri* __restrict__ tris) {
     constexpr unsigned kAll = 0xFFFFFFFFu;
     const unsigned marching = __ballot_sync(kAll, ok);
     if (marching == 0) return true;
@@ -396,22 +392,20 @@ __device__ __forceinline__ bool walk_warp(bool& ok, RayState& r, const Traversal
     const int first = __shfl_sync(kAll, oct, __ffs(marching) - 1);
     const bool uniform = __all_sync(kAll, !ok || oct == first);
     if (!ok) return uniform;
-    bool done;
     if (uniform) {
         switch (first) {
-            case 0: done = walk<CellT, 0, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 1: done = walk<CellT, 1, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 2: done = walk<CellT, 2, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 3: done = walk<CellT, 3, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 4: done = walk<CellT, 4, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 5: done = walk<CellT, 5, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            case 6: done = walk<CellT, 6, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
-            default: done = walk<CellT, 7, kBudget>(r, P, entries, cells, ref_ids, tris, limit); break;
+            case 0: walk<CellT, 0>(r, P, entries, cells, ref_ids, tris); break;
+            case 1: walk<CellT, 1>(r, P, entries, cells, ref_ids, tris); break;
+            case 2: walk<CellT, 2>(r, P, entries, cells, ref_ids, tris); break;
+            case 3: walk<CellT, 3>(r, P, entries, cells, ref_ids, tris); break;
+            case 4: walk<CellT, 4>(r, P, entries, cells, ref_ids, tris); break;
+            case 5: walk<CellT, 5>(r, P, entries, cells, ref_ids, tris); break;
+            case 6: walk<CellT, 6>(r, P, entries, cells, ref_ids, tris); break;
+            default: walk<CellT, 7>(r, P, entries, cells, ref_ids, tris); break;
         }
     } else {
-        done = walk<CellT, -1, kBudget>(r, P, entries, cells, ref_ids, tris, limit);
+        walk<CellT, -1>(r, P, entries, cells, ref_ids, tris);
     }
-    ok = !done;
     return uniform;
 }
 
@@ -438,289 +432,17 @@ __device__ __forceinline__ int fetch_tile(unsigned* __restrict__ next_tile, unsi
 #ifdef HGB_TILE_TRACE
 // Diagnosis build only (tools/gpu_tile_variants.py): per warp [first tile started, last tile finished, tiles traced], ns
 __device__ long long g_tile_trace[3 * 8192];
-__device__ unsigned long long g_split_stats[8];   // marches, segments, loop iterations, rounds, -, ns inside split_walk
 __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
-// ---------------------------------------------------------------------------
-// Stragglers. A launch is over when its longest ray is over: on the 7.8 M-triangle scene the mean primary ray takes 8
-// steps, the longest 347 (155 cells, each a chain of dependent L2 / DRAM round trips), and that one ray lasts as long
-// as the rest of the frame together -- the queue of tiles is empty after 65 us, the launch ends after 210 us with a
-// handful of lanes marching (tools/gpu_tile_timeline.py). The reference has no answer to that (one thread per ray,
-// src/traverse.cu:28-38); shards of a frame inherit the same tail, which is what limits strong scaling.
-//
-//   * a ray that has taken more than `budget` steps is PARKED: its state (64 bytes) goes into a queue in device
-//     memory and its lane is free for the next tile / the next ray;
-//   * warps that run out of regular work SERVE the queue, one ray per warp, with a split march: what is left of the
-//     ray is worked off in rounds; a round cuts the next stretch of the ray into up to 32 segments, one per lane. Lane 0
-//     continues from the exact state; lane g starts from the voxel recomputed at its cut point and enters that cell
-//     WITHOUT testing it, which leaves it in a state (voxel, hit in hand) the exact march may or may not pass through;
-//   * all lanes march in step. A lane records the first four states it passes as marks. The march is a pure function
-//     of the state (voxel, hit in hand): as soon as lane g stands in a state equal to a mark of lane g+1, with the hit
-//     the round started with unchanged on both sides, everything lane g+1 did from that mark on IS what lane g would
-//     do next, and lane g stops ("joined"). Cells overlap after expand_grid, so two marches of one ray can take a few
-//     cells to fall into step: over the 40 000 longest rays of that frame the join happens at mark 0 in 85 %, within
-//     four marks in all but 0.005 % (CPU model of this procedure: oracle og_traverse_split). A lane that finds no mark
-//     simply marches on: slower, never different;
-//   * the result is read off the chain: lanes 0 .. c-1 joined, lane c ended (hit, or left the grid) or is the round's
-//     last lane and reports where it stands: steps = what every lane of the chain contributed between its entry point
-//     and its join; the next round starts from lane c's state, which is the ray's true state.
-//
-// Every float operation that decides anything is the march's own (visit_cell); where the cuts are placed changes
-// speed, not results. tests/: ids, t and step counts bit-identical to the reference with the budget set so low that
-// most rays of a frame go through the queue. Parking is used for scenes that do not fit the L2 (a march through a
-// resident scene has no such tail: the C2 frame's longest ray takes 112 steps).
-// ---------------------------------------------------------------------------
-struct SplitParams {
-    int budget;          // steps after which a ray is parked
-    int voxels;          // finest voxels along the ray's dominant axis per segment
-    int max_segments;    // segments (lanes) of a round
-};
-
-/// A parked ray (four 16-byte words). `ready` carries the launch's epoch: the array never has to be cleared.
-struct ParkedRay {
-    float ox, oy, oz, tmin;
-    float dx, dy, dz, hit_t;
-    int   vx, vy, vz, hit_id;
-    float tlast; int steps; int ray; unsigned ready;
-};
-static_assert(sizeof(ParkedRay) == 64, "four 16-byte words");
-
-struct StragglerQueue {
-    ParkedRay* slots;
-    unsigned capacity;           // 0: nothing is parked
-    unsigned* counters;          // [0] parked so far, [1] taken so far, [2] warps that have left their regular work (zeroed by the host)
-    unsigned epoch;
-};
-
-constexpr int kSplitMarks = 4;
-
-__device__ __forceinline__ unsigned long long pack_voxel(const RayState& r) {
-    // states inside the grid only (virtual dims <= 2^21, checked on the host)
-    return (unsigned long long)unsigned(r.vx) | ((unsigned long long)unsigned(r.vy) << 21) | ((unsigned long long)unsigned(r.vz) << 42);
-}
-
-__device__ __forceinline__ unsigned load_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
-
-/// Lane-local: parks ray `id` in `slot` (interrupted by its budget, r.tlast set). False when the queue is full.
-__device__ __forceinline__ bool park_ray(const StragglerQueue& Q, unsigned slot, const RayState& r, int id) {
-    if (slot >= Q.capacity) return false;
-    ParkedRay* dst = Q.slots + slot;
-    float4* w = reinterpret_cast<float4*>(dst);
-    w[0] = make_float4(r.ox, r.oy, r.oz, r.tmin);
-    w[1] = make_float4(r.dx, r.dy, r.dz, r.hit_t);
-    reinterpret_cast<int4*>(w)[2] = make_int4(r.vx, r.vy, r.vz, r.hit_id);
-    dst->tlast = r.tlast; dst->steps = r.steps; dst->ray = id;
-    __threadfence();
-    *reinterpret_cast<volatile unsigned*>(&dst->ready) = Q.epoch;
-    return true;
-}
-
-struct SplitResult { float hit_t; int hit_id; int steps; };
-
-/// All 32 lanes, with a parked ray broadcast to all: finishes that ray; returns its final hit and the steps taken from
-/// here on.
-template <typename CellT>
-__device__ __forceinline__ SplitResult split_walk(float ox, float oy, float oz, float tmin, float dx, float dy, float dz,
-                                                  float hit_t0, int hit_id0, int vx, int vy, int vz, float t0,
-                                                  const TraversalParams& P, const SplitParams& S,
-                                                  const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
-                                                  const int* __restrict__ ref_ids, const Tri* __restrict__ tris) {
-    using namespace dev;
-    constexpr unsigned kAll = 0xFFFFFFFFu;
-    constexpr int kLastCells = 4;          // cells the last segment of a round marches beyond its recorded ones
-    const int lane = threadIdx.x & 31;
-    RayState q;
-    q.ox = ox; q.oy = oy; q.oz = oz; q.tmin = tmin; q.dx = dx; q.dy = dy; q.dz = dz;
-    q.ix = safe_rcp(q.dx); q.iy = safe_rcp(q.dy); q.iz = safe_rcp(q.dz);
-    // plain float arithmetic below places the cuts; it decides nothing
-    const float far_t = fminf(sel_max((P.min_x - q.ox) * q.ix, (P.max_x - q.ox) * q.ix),
-                              fminf(sel_max((P.min_y - q.oy) * q.iy, (P.max_y - q.oy) * q.iy),
-                                    sel_max((P.min_z - q.oz) * q.iz, (P.max_z - q.oz) * q.iz)));
-    const float speed = fmaxf(fabsf(q.dx) * P.inv_x, fmaxf(fabsf(q.dy) * P.inv_y, fabsf(q.dz) * P.inv_z));   // finest voxels per unit t
-    const float segment_t = float(S.voxels) / speed;
-    int steps_total = 0;
-#ifdef HGB_TILE_TRACE
-    int iterations = 0, rounds = 0, segments = 0;
-    const long long entered = global_ns();
-#endif
-
-    while (true) {
-        // ---- one round, from the exact state (vx, vy, vz, t0, hit in hand)
-        const float reach = (fminf(far_t, hit_t0) - t0) * speed;
-        int count = 1;
-        if (reach > 0.0f && reach < 1e9f && segment_t > 0.0f) count = min(S.max_segments, int(reach / float(S.voxels)) + 1);
-#ifdef HGB_TILE_TRACE
-        rounds++; segments += count;
-#endif
-        q.vx = vx; q.vy = vy; q.vz = vz;
-        q.hit_t = hit_t0; q.hit_id = hit_id0; q.steps = 0; q.tlast = t0;
-        if (count < 2) {
-            // nothing to share out: lane 0 marches to the end of the ray
-            if (lane == 0) walk<CellT, -1, false>(q, P, entries, cells, ref_ids, tris);
-            hit_t0 = __shfl_sync(kAll, q.hit_t, 0);
-            hit_id0 = __shfl_sync(kAll, q.hit_id, 0);
-            steps_total += __shfl_sync(kAll, q.steps, 0);
-            break;
-        }
-
-        // 0 = marching, 1 = ended (hit or left the grid: final), 2 = joined the next segment, 3 = interrupted (last segment)
-        int state = lane < count ? 0 : 1;
-        if (lane > 0 && lane < count) {
-            const float ts = t0 + segment_t * float(lane);
-            q.vx = min(P.dims_x - 1, max(0, trunc_to_int(mul(sub(fma(q.dx, ts, q.ox), P.min_x), P.inv_x))));
-            q.vy = min(P.dims_y - 1, max(0, trunc_to_int(mul(sub(fma(q.dy, ts, q.oy), P.min_y), P.inv_y))));
-            q.vz = min(P.dims_z - 1, max(0, trunc_to_int(mul(sub(fma(q.dz, ts, q.oz), P.min_z), P.inv_z))));
-            CellBox untested;
-            enter_cell<CellT, -1>(q, P, entries, cells, untested);
-            if (left_grid(q, P)) state = 1;              // a state the march can only reach by ending: nobody joins it
-        }
-
-        unsigned long long mark[kSplitMarks], next_mark[kSplitMarks];
-        int mark_steps[kSplitMarks], next_steps[kSplitMarks];
-        int marks = 0;
-#pragma unroll
-        for (int i = 0; i < kSplitMarks; i++) { mark[i] = ~0ull; mark_steps[i] = 0; }
-        auto clean = [&] { return q.hit_id == hit_id0 && q.hit_t == hit_t0; };
-        auto advance = [&] {
-            const float texit = visit_cell<CellT, -1>(q, P, entries, cells, ref_ids, tris);
-            q.tlast = texit;
-            if (q.hit_t <= texit || left_grid(q, P)) state = 1;
-        };
-        // the first cells of every segment, their states recorded (while the hit in hand is the one the round started with)
-#pragma unroll
-        for (int i = 0; i < kSplitMarks; i++) {
-            if (state == 0) {
-                if (marks == i && clean()) { mark[i] = pack_voxel(q); mark_steps[i] = q.steps; marks = i + 1; }
-                advance();
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kSplitMarks; i++) {
-            next_mark[i] = __shfl_down_sync(kAll, mark[i], 1);
-            next_steps[i] = __shfl_down_sync(kAll, mark_steps[i], 1);
-        }
-        int next_marks = __shfl_down_sync(kAll, marks, 1);
-        if (lane + 1 >= count) next_marks = 0;
-
-        int own_steps = 0;       // steps this lane contributes, up to where it joined
-        int join_skip = 0;       // steps the next lane had already taken at the mark this lane joined
-        // did one of the states just recorded already stand on a mark of the next segment?
-        if (state == 0) {
-#pragma unroll
-            for (int j = kSplitMarks - 1; j >= 0; j--)
-#pragma unroll
-                for (int k = 0; k < kSplitMarks; k++)
-                    if (j < marks && k < next_marks && mark[j] == next_mark[k]) { state = 2; own_steps = mark_steps[j]; join_skip = next_steps[k]; }
-        }
-
-        int last = 0;            // lane the chain ends in
-        int extra = 0;           // cells the last segment has marched beyond the recorded ones
-        while (true) {
-#ifdef HGB_TILE_TRACE
-            iterations++;
-#endif
-            const unsigned stopped = __ballot_sync(kAll, state == 1 || state == 3), joined = __ballot_sync(kAll, state == 2);
-            if (stopped) {
-                last = __ffs(stopped) - 1;
-                const unsigned before = (1u << last) - 1u;
-                if ((joined & before) == before) break;  // lanes 0 .. last-1 joined, lane `last` ended or stands: the chain is complete
-            }
-            if (state == 0) {
-                if (clean()) {
-                    const unsigned long long here = pack_voxel(q);
-#pragma unroll
-                    for (int k = 0; k < kSplitMarks; k++)
-                        if (k < next_marks && here == next_mark[k]) { state = 2; own_steps = q.steps; join_skip = next_steps[k]; }
-                }
-                if (state == 0) {
-                    if (lane == count - 1 && extra++ >= kLastCells) state = 3;
-                    else advance();
-                }
-            }
-        }
-
-        if (state == 1 || state == 3) own_steps = q.steps;
-        const int skip = __shfl_up_sync(kAll, join_skip, 1);
-        int total = lane <= last ? own_steps - (lane > 0 ? skip : 0) : 0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(kAll, total, d);
-        steps_total += total;
-        hit_t0 = __shfl_sync(kAll, q.hit_t, last);
-        hit_id0 = __shfl_sync(kAll, q.hit_id, last);
-        if (__shfl_sync(kAll, state, last) == 1) break;
-        // the chain's last lane stands in the ray's true state: the next round starts there
-        vx = __shfl_sync(kAll, q.vx, last); vy = __shfl_sync(kAll, q.vy, last); vz = __shfl_sync(kAll, q.vz, last);
-        t0 = __shfl_sync(kAll, q.tlast, last);
-    }
-#ifdef HGB_TILE_TRACE
-    if (lane == 0) {
-        atomicAdd(g_split_stats + 0, 1ull); atomicAdd(g_split_stats + 1, (unsigned long long)segments);
-        atomicAdd(g_split_stats + 2, (unsigned long long)iterations); atomicAdd(g_split_stats + 3, (unsigned long long)rounds);
-        atomicAdd(g_split_stats + 5, (unsigned long long)(global_ns() - entered));
-    }
-#endif
-    SplitResult res;
-    res.hit_t = hit_t0;
-    res.hit_id = hit_id0;
-    res.steps = steps_total;
-    return res;
-}
-
-/// Called by every warp of a launch when it has run out of regular work (all 32 lanes): takes parked rays one at a
-/// time and finishes each with all its lanes, until every warp has left its regular work and every parked ray has
-/// been taken. `warps` = warps of the launch.
 template <typename CellT, bool kPrimId>
-__device__ __forceinline__ void serve_parked(const StragglerQueue& Q, const TraversalParams& P, const SplitParams& S, unsigned warps,
-                                             const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
-                                             const int* __restrict__ ref_ids, const Tri* __restrict__ tris, Hit* __restrict__ hits) {
-    constexpr unsigned kAll = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-    __threadfence();
-    if (lane == 0) atomicAdd(Q.counters + 2, 1u);
-    while (true) {
-        unsigned take = 0;
-        if (lane == 0) take = atomicAdd(Q.counters + 1, 1u);
-        take = __shfl_sync(kAll, take, 0);
-        if (take >= Q.capacity) break;
-        const ParkedRay* src = Q.slots + take;
-        bool have = false;
-        while (true) {
-            if (load_volatile(&src->ready) == Q.epoch) { have = true; break; }
-            if (load_volatile(Q.counters + 2) == warps) {
-                // nobody parks any more: the slot is either filled (and visible) or will never be
-                __threadfence();
-                have = take < min(load_volatile(Q.counters), Q.capacity);
-                break;
-            }
-            __nanosleep(256);
-        }
-        if (!have) break;
-        __threadfence();
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(src) + 0);
-        const float4 b = __ldcg(reinterpret_cast<const float4*>(src) + 1);
-        const int4 c = __ldcg(reinterpret_cast<const int4*>(src) + 2);
-        const int4 d = __ldcg(reinterpret_cast<const int4*>(src) + 3);
-        const SplitResult res = split_walk<CellT>(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.w, c.x, c.y, c.z, __int_as_float(d.x),
-                                                  P, S, entries, cells, ref_ids, tris);
-        if (lane == 0)
-            dev::stg4_stream(hits + d.z, make_float4(__int_as_float(kPrimId ? res.hit_id : d.y + res.steps), res.hit_t, 0.0f, 0.0f));
-    }
-}
-
-/// kPark: tiles march for S.budget steps; rays that are not done by then are parked, and a warp that finds the tile
-/// queue empty serves the parked rays (see "Stragglers" above).
-constexpr int kParkTileBlocksPerSm = 10;     // the parking variant carries the split march: 51 registers instead of 40
-
-template <typename CellT, bool kPrimId, bool kPark>
-__global__ void __launch_bounds__(kTileBlock, kPark ? kParkTileBlocksPerSm : kTileBlocksPerSm)
+__global__ void __launch_bounds__(kTileBlock, kTileBlocksPerSm)
 traverse_tiles(const __grid_constant__ TraversalParams P,
                const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
                const int* __restrict__ layout, int host_width, unsigned* __restrict__ next_tile, unsigned ticket_base,
-               int* __restrict__ feedback, const __grid_constant__ SplitParams S, const __grid_constant__ StragglerQueue Q) {
-    constexpr unsigned kAll = 0xFFFFFFFFu;
+               int* __restrict__ feedback) {
     const int lane = threadIdx.x & 31;
     // feedback (device memory, may be null): [0] += warps whose rays did not share a direction octant, [1] += 1
     // per launch. A buffer of camera rays has a few such warps along the image axes; a buffer whose warps are
@@ -739,28 +461,22 @@ traverse_tiles(const __grid_constant__ TraversalParams P,
     while (tile < num_tiles) {
         RayState r;
         bool ok = false;
-        int id = tile * 32 + lane;
-        if (id < num_rays) {
-            if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
-            ok = start_ray(r, P, rays, id);
-        } else {
-            id = -1;
-        }
-        const bool uniform = walk_warp<CellT, kPark>(ok, r, P, entries, cells, ref_ids, tris, S.budget);
-        if (!uniform && feedback && lane == 0) atomicAdd(feedback, 1);
-        if (kPark) {
-            const unsigned rest = __ballot_sync(kAll, ok);
-            if (rest) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(Q.counters, unsigned(__popc(rest)));
-                base = __shfl_sync(kAll, base, 0);
-                if (ok) {
-                    if (park_ray(Q, base + __popc(rest & ((1u << lane) - 1u)), r, id)) id = -1;    // whoever takes the slot writes the hit
-                    else walk<CellT, -1, false>(r, P, entries, cells, ref_ids, tris);              // queue full: finish here
-                }
+        {
+            int id = tile * 32 + lane;
+            if (id < num_rays) {
+                if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
+                ok = start_ray(r, P, rays, id);
             }
         }
-        if (id >= 0) finish_ray<kPrimId>(r, hits, id);
+        const bool uniform = walk_warp(ok, r, P, entries, cells, ref_ids, tris);
+        if (!uniform && feedback && lane == 0) atomicAdd(feedback, 1);
+        {   // the ray's place in the buffer again (cheaper than keeping it in a register across the march)
+            int id = tile * 32 + lane;
+            if (id < num_rays) {
+                if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
+                finish_ray<kPrimId>(r, hits, id);
+            }
+        }
         __syncwarp();
 #ifdef HGB_TILE_TRACE
         traced_tiles++;
@@ -768,7 +484,6 @@ traverse_tiles(const __grid_constant__ TraversalParams P,
 #endif
         tile = fetch_tile(next_tile, ticket_base, first_dynamic, lane);
     }
-    if (kPark) serve_parked<CellT, kPrimId>(Q, P, S, gridDim.x * (kTileBlock / 32), entries, cells, ref_ids, tris, hits);
 }
 
 // ---------------------------------------------------------------------------
@@ -896,16 +611,13 @@ constexpr int kVoteRefillMinLanes = 4;
 constexpr int kVoteTurn = 3;            // references a lane tests per triangle turn
 constexpr int kVoteBlocksPerSm = 10;    // <= 51 registers
 
-template <typename CellT, bool kPrimId, bool kPark>
+template <typename CellT, bool kPrimId>
 __global__ void __launch_bounds__(kBlockThreads, kVoteBlocksPerSm)
 traverse_voting(const __grid_constant__ TraversalParams P,
                 const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                 const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                 const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
-                int* __restrict__ next_ray, const int* __restrict__ order,
-                const __grid_constant__ SplitParams S, const __grid_constant__ StragglerQueue Q) {
-    // kPark: a ray that has taken S.budget steps is parked at its next cell boundary (its lane is refilled), and the
-    // warp serves the parked rays once no regular work is left (see "Stragglers")
+                int* __restrict__ next_ray, const int* __restrict__ order) {
     // `order` (may be null): the k-th ray handed out is rays[order[k]] (ray binning, see bin_rays); hits go to the
     // ray's own slot, so the caller sees nothing of it
     constexpr bool kSentinel = sizeof(CellT) == sizeof(SmallCell);
@@ -967,14 +679,9 @@ traverse_voting(const __grid_constant__ TraversalParams P,
                     ref = cur < end ? __ldg(ref_ids + cur++) : -1;
                     r.steps += 1 + (cell.end - cell.begin);
                 }
-                if (ref < 0) {
-                    if (r.hit_t <= texit || outside(r, P)) {
-                        finish_ray<kPrimId>(r, hits, ray_id);
-                        ray_id = -1;
-                    } else if (kPark && r.steps >= S.budget) {
-                        r.tlast = texit;
-                        if (park_ray(Q, atomicAdd(Q.counters, 1u), r, ray_id)) ray_id = -1;
-                    }
+                if (ref < 0 && (r.hit_t <= texit || outside(r, P))) {
+                    finish_ray<kPrimId>(r, hits, ray_id);
+                    ray_id = -1;
                 }
             }
         } else if (ref >= 0) {
@@ -993,18 +700,12 @@ traverse_voting(const __grid_constant__ TraversalParams P,
 #pragma unroll
             for (int k = 0; k < kVoteTurn; k++)
                 if (batch[k] >= 0) intersect_tri(r, tris, batch[k]);
-            if (ref < 0) {
-                if (r.hit_t <= texit || outside(r, P)) {
-                    finish_ray<kPrimId>(r, hits, ray_id);
-                    ray_id = -1;
-                } else if (kPark && r.steps >= S.budget) {
-                    r.tlast = texit;
-                    if (park_ray(Q, atomicAdd(Q.counters, 1u), r, ray_id)) ray_id = -1;
-                }
+            if (ref < 0 && (r.hit_t <= texit || outside(r, P))) {
+                finish_ray<kPrimId>(r, hits, ray_id);
+                ray_id = -1;
             }
         }
     }
-    if (kPark) serve_parked<CellT, kPrimId>(Q, P, S, gridDim.x * (kBlockThreads / 32), entries, cells, ref_ids, tris, hits);
 }
 
 /// A tile counter in device memory and the value the host knows it to have (fetch_tile)
@@ -1040,9 +741,6 @@ struct DeviceState {
     unsigned long long launches = 0;
     int* seen_host = nullptr;        // pinned block behind seen[].host
     int num_sms = 0;
-    ParkedRay* parked = nullptr;     // straggler queue of launches on the default stream (and on the frame chain's stream)
-    unsigned parked_capacity = 0, parked_epoch = 0;
-    unsigned* parked_counters = nullptr;
     int* sort_scratch = nullptr;     // ray binning ("ray_sort"): keys, order and the sort's scratch
     size_t sort_capacity = 0;
     // host-buffer frames (traverse_grid_host): one upload stream, one download stream, two traversal streams
@@ -1065,9 +763,8 @@ DeviceState& device_state() {
     DeviceState& st = states[dev];
     std::lock_guard<std::mutex> guard(init_lock);
     if (!st.words) {
-        HGB_CUDA(cudaMalloc(&st.words, 320));
-        HGB_CUDA(cudaMemset(st.words, 0, 320));
-        st.parked_counters = reinterpret_cast<unsigned*>(st.words + 64);
+        HGB_CUDA(cudaMalloc(&st.words, 256));
+        HGB_CUDA(cudaMemset(st.words, 0, 256));
         st.vote_counter = st.words;
         st.tiles.word = reinterpret_cast<unsigned*>(st.words + 8);
         st.stream_vote_counters[0] = st.words + 16;
@@ -1140,66 +837,27 @@ __global__ void __launch_bounds__(256) ray_bin_keys(const __grid_constant__ Trav
 
 std::atomic<int> g_ray_sort{0};
 
-// Stragglers: step budget after which a ray is parked (0: never), segment length and segments per round of the split
-// march, and the scene size (MB) above which parking is used at all (a march through an L2-resident scene has no such tail)
-std::atomic<int> g_split_budget{128}, g_split_voxels{64}, g_split_segments{32}, g_park_scene_mb{64};
-
-/// The straggler queue for a launch over `num_rays` rays enqueued on `stream` (null capacity: nothing is parked). One
-/// queue per device: only for launches that cannot overlap each other.
-StragglerQueue straggler_queue(DeviceState& st, const Grid& grid, const TraversalParams& P, size_t cell_bytes, int num_rays, cudaStream_t stream) {
-    StragglerQueue Q = {};
-    if (g_split_budget.load() <= 0 || max(P.dims_x, max(P.dims_y, P.dims_z)) > (1 << 21)) return Q;      // pack_voxel
-    const size_t scene = size_t(grid.num_entries) * 4 + size_t(grid.num_cells) * cell_bytes + size_t(grid.num_refs) * 4;
-    if (scene < size_t(g_park_scene_mb.load()) << 20) return Q;
-    const unsigned want = unsigned(std::max(num_rays / 8, 1 << 16));
-    if (want > st.parked_capacity) {
-        if (st.parked) HGB_CUDA(cudaFree(st.parked));
-        HGB_CUDA(cudaMalloc(&st.parked, sizeof(ParkedRay) * size_t(want)));
-        HGB_CUDA(cudaMemsetAsync(st.parked, 0, sizeof(ParkedRay) * size_t(want), stream));
-        st.parked_capacity = want;
-        st.parked_epoch = 0;
-    }
-    if (++st.parked_epoch == 0) {       // wrapped: the flags of 2^32 launches ago must not look fresh
-        HGB_CUDA(cudaMemsetAsync(st.parked, 0, sizeof(ParkedRay) * size_t(st.parked_capacity), stream));
-        st.parked_epoch = 1;
-    }
-    HGB_CUDA(cudaMemsetAsync(st.parked_counters, 0, 4 * sizeof(unsigned), stream));
-    Q.slots = st.parked; Q.capacity = st.parked_capacity; Q.counters = st.parked_counters; Q.epoch = st.parked_epoch;
-    return Q;
-}
-
 /// Enqueues one traversal launch on `stream`: 1 = persistent voting warps (needs `vote_counter`), 4 = resident
 /// warps pulling tiles (needs `ticket`), otherwise one thread per ray; 2 and 4 re-tile by the raster width in
 /// `layout[0]` (device) or `host_width`.
 template <typename CellT, bool kPrimId>
 void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays,
              int variant, const int* layout, int host_width, int* vote_counter, Ticket& ticket, int num_sms, cudaStream_t stream,
-             int* feedback = nullptr, const int* order = nullptr, DeviceState* park_in = nullptr) {
+             int* feedback = nullptr, const int* order = nullptr) {
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
     const TraversalParams P = params_of(grid);
-    const SplitParams S = {g_split_budget.load(), g_split_voxels.load(), g_split_segments.load()};
-    const StragglerQueue Q = park_in && (variant == 4 || variant == 1) ? straggler_queue(*park_in, grid, P, sizeof(CellT), num_rays, stream) : StragglerQueue{};
     if (variant == 4) {
-        const int blocks = min(num_sms * (Q.capacity ? kParkTileBlocksPerSm : kTileBlocksPerSm), round_div(num_rays, kTileBlock));
-        if (Q.capacity)
-            traverse_tiles<CellT, kPrimId, true><<<blocks, kTileBlock, 0, stream>>>(
-                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback, S, Q);
-        else
-            traverse_tiles<CellT, kPrimId, false><<<blocks, kTileBlock, 0, stream>>>(
-                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback, S, Q);
+        const int blocks = min(num_sms * kTileBlocksPerSm, round_div(num_rays, kTileBlock));
+        traverse_tiles<CellT, kPrimId><<<blocks, kTileBlock, 0, stream>>>(
+            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback);
         ticket.base += unsigned((num_rays + 31) >> 5);      // one fetch per traced tile (fetch_tile)
         count_launch();
     } else if (variant == 1) {
         HGB_CUDA(cudaMemsetAsync(vote_counter, 0, sizeof(int), stream));
         // every warp reserves two blocks of rays up front: no more warps than there are blocks
         const int blocks = max(1, min(num_sms * kVoteBlocksPerSm, round_div(num_rays, 2 * kVoteBlock * (kBlockThreads / 32))));
-        if (Q.capacity)
-            traverse_voting<CellT, kPrimId, true><<<blocks, kBlockThreads, 0, stream>>>(
-                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, vote_counter, order, S, Q);
-        else
-            traverse_voting<CellT, kPrimId, false><<<blocks, kBlockThreads, 0, stream>>>(
-                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, vote_counter, order, S, Q);
-        count_launch();
+        traverse_voting<CellT, kPrimId><<<blocks, kBlockThreads, 0, stream>>>(
+            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, vote_counter, order); count_launch();
     } else {
         traverse_per_thread<CellT, kPrimId><<<round_div(num_rays, 128), 128, 0, stream>>>(
             P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width); count_launch();
@@ -1301,7 +959,7 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
         order = prim::sort_pairs(keys, idx, keys_alt, idx_alt, num_rays, bits, idx_alt + num_rays) ? idx_alt : idx;
     }
     enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, tiled && buf ? buf->layout : nullptr, 0,
-                            st.vote_counter, st.tiles, st.num_sms, 0, feedback, order, &st);
+                            st.vote_counter, st.tiles, st.num_sms, 0, feedback, order);
     if (feedback) {
         // copied back after launches 1, 2, 4 and then every 8th: one 8-byte copy in eight launches
         const int tick = ++buf->feedback_tick;
@@ -1505,14 +1163,13 @@ void launch_two_waves(const Grid& grid, const CellT* cells, const Tri* tris, int
             if (width <= 0) first = 0;
             second = 0;
         }
-        DeviceState* park_in = chunks == 1 ? &st : nullptr;      // one chain: its launches cannot overlap each other
         enqueue<CellT, true>(grid, cells, tris, rays + begin, hits_primary + begin, count, first, nullptr, width,
-                             st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run, nullptr, nullptr, park_in);
+                             st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
         if (counters) count_hits_on(run, hits_primary + begin, count, counters);
         generate_bounce_rays_on(run, tris, num_tris, rays + begin, hits_primary + begin, count, offset, tmax, seed, bounce + begin,
                                 keys ? keys + begin : nullptr, int(begin));
         enqueue<CellT, true>(grid, cells, tris, bounce + begin, hits_bounce + begin, count, second, nullptr, 0,
-                             st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run, nullptr, nullptr, park_in);
+                             st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
         if (counters) count_hits_on(run, hits_bounce + begin, count, counters);
     }
     HGB_CUDA(cudaGetLastError());
@@ -1599,10 +1256,6 @@ bool set_traversal_option(const char* key, int value) {
     if (!std::strcmp(key, "traverse_variant")) { g_variant.store(value); return true; }
     if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk.store(value > 0 ? value : 256 * 1024); return true; }
     if (!std::strcmp(key, "ray_sort")) { g_ray_sort.store(value != 0); return true; }
-    if (!std::strcmp(key, "split_budget")) { g_split_budget.store(value >= 0 ? value : 128); return true; }
-    if (!std::strcmp(key, "split_voxels")) { g_split_voxels.store(value > 0 ? value : 64); return true; }
-    if (!std::strcmp(key, "split_segments")) { g_split_segments.store(value > 1 ? min(value, 32) : 32); return true; }
-    if (!std::strcmp(key, "park_scene_mb")) { g_park_scene_mb.store(value >= 0 ? value : 64); return true; }
     if (!std::strcmp(key, "two_wave_chunks")) { g_two_wave_chunks.store(value > 0 ? min(value, 16) : 1); return true; }
     if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (1280 << 10)); return true; }
     return false;
@@ -1652,10 +1305,5 @@ void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays,
 #ifdef HGB_TILE_TRACE
 extern "C" __attribute__((visibility("default"))) int hgb_debug_tile_trace(long long* out) {
     return cudaMemcpyFromSymbol(out, hagrid::g_tile_trace, sizeof(long long) * 3 * 8192) == cudaSuccess ? 0 : -1;
-}
-extern "C" __attribute__((visibility("default"))) int hgb_debug_split_stats(unsigned long long* out, int reset) {
-    if (cudaMemcpyFromSymbol(out, hagrid::g_split_stats, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
-    if (reset) { unsigned long long zero[8] = {}; cudaMemcpyToSymbol(hagrid::g_split_stats, zero, sizeof(zero)); }
-    return 0;
 }
 #endif

@@ -15,9 +15,7 @@ sc = Scene(tris, keep_alive=True, lib=lib); sc.build_all(0.15, 3.0); sc.setup_tr
 d_rays = torch.from_numpy(rays.view(np.float32).reshape(n, 8)).cuda(); d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
 for k, v in (a.split("=") for a in sys.argv[2:]):
     lib.set_option(k, int(v))
-stats = np.zeros(8, dtype=np.uint64)
 for rep in range(4):
-    lib.dll.hgb_debug_split_stats(C.c_void_p(stats.ctypes.data), 1)
     flush.zero_(); a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
     a.record(); sc.traverse(d_rays, d_hits, n, HIT_PRIM_ID); b.record(); torch.cuda.synchronize()
     buf = np.zeros(3 * 8192, dtype=np.int64)
@@ -29,10 +27,6 @@ for rep in range(4):
     print(f"rep {rep}: event {a.elapsed_time(b) * 1e3:.1f} us | warp starts p50 {q(start, 50):.1f} p99 {q(start, 99):.1f} max {start.max():.1f} | "
           f"warp ends p1 {q(end, 1):.1f} p10 {q(end, 10):.1f} p50 {q(end, 50):.1f} p90 {q(end, 90):.1f} p99 {q(end, 99):.1f} max {end.max():.1f} | "
           f"tiles/warp min {cnt.min()} mean {cnt.mean():.1f} max {cnt.max()}", flush=True)
-    lib.dll.hgb_debug_split_stats(C.c_void_p(stats.ctypes.data), 1)
-    if stats[0]:
-        c = float(stats[0])
-        print(f"   split marches: {int(stats[0])}, segments {stats[1] / c:.1f}, loop iterations {stats[2] / c:.1f}, rounds {stats[3] / c:.1f}, us per march {stats[5] / c / 1e3:.2f}")
     # active warps over time
     grid_t = np.linspace(0, end.max(), 21)
     act = [(int(((start <= x) & (end > x)).sum())) for x in grid_t]
