@@ -936,184 +936,3 @@ void og_bounce_rays(const og_tri* tris, int num_tris, const og_ray* rays, const 
         out[i] = o;
     }
 }
-
-/* ------------------------------------------------------------------ split walk of long rays (model of hagrid_b200's straggler path)
- * Not part of the reference: the reference walks every ray serially (src/traverse.cu:56-90). hagrid_b200 hands the rest of a long
- * ray to the idle lanes of its warp: the remaining parameter interval is cut into segments, every segment is walked from a voxel
- * recomputed at its start, and a segment ends where its state (voxel, hit) equals the verified start state of the next one. This
- * function restates that procedure on the CPU so that tests can check two things without a GPU: the result equals the serial
- * walk's bit for bit whatever the cut points are, and how long the critical path (longest segment) is.
- * stats (per ray, 4 ints): cells of the serial walk, cells on the critical path of the split walk (prefix + longest segment),
- * segments of the chain that produced the result, segments started. */
-typedef struct { int voxel[3]; og_hit hit; int steps, cells; float texit; } og_walk;
-
-typedef struct {
-    const og_grid* g; const og_tri* tris; const og_ray* ray;
-    int dims[3]; float ginv[3], csize[3], inv[3];
-} og_ctx;
-
-static void ctx_init(og_ctx* c, const og_grid* g, const og_tri* tris, const og_ray* ray) {
-    c->g = g; c->tris = tris; c->ray = ray;
-    for (int k = 0; k < 3; k++) {
-        c->dims[k] = g->dims[k] << g->shift;
-        const float ext = g->bbox_max[k] - g->bbox_min[k];
-        c->ginv[k] = (float)c->dims[k] / ext;
-        c->csize[k] = ext / (float)c->dims[k];
-        c->inv[k] = safe_rcp(ray->dir[k]);
-    }
-}
-
-static void voxel_at(const og_ctx* c, float t, int* voxel) {
-    for (int k = 0; k < 3; k++)
-        voxel[k] = imin(c->dims[k] - 1, imax(0, f2i((fmaf(c->ray->dir[k], t, c->ray->org[k]) - c->g->bbox_min[k]) * c->ginv[k])));
-}
-
-/* One cell of src/traverse.cu:57-90; `test` = 0 skips the triangles (the first cell of a segment only fixes its start state).
- * Returns 1 when the ray ends here. */
-static int walk_cell(const og_ctx* c, og_walk* w, int test) {
-    const og_grid* g = c->g; const float* org = c->ray->org; const float* dir = c->ray->dir;
-    const int cell_id = lookup(g->entries, g->shift, g->dims[0], g->dims[1], w->voxel[0], w->voxel[1], w->voxel[2]);
-    int cmin[3], cmax[3], begin, end;
-    if (g->compressed) {
-        const og_small_cell* s = g->small_cells + cell_id;
-        for (int k = 0; k < 3; k++) { cmin[k] = s->min[k]; cmax[k] = s->max[k]; }
-        begin = s->begin; end = -1;
-    } else {
-        const og_cell* s = g->cells + cell_id;
-        for (int k = 0; k < 3; k++) { cmin[k] = s->min[k]; cmax[k] = s->max[k]; }
-        begin = s->begin; end = s->end;
-    }
-    int point[3]; float tc[3];
-    for (int k = 0; k < 3; k++) {
-        point[k] = dir[k] >= 0.0f ? cmax[k] : cmin[k];
-        tc[k] = (fmaf((float)point[k], c->csize[k], g->bbox_min[k]) - org[k]) * c->inv[k];
-    }
-    const float texit = fminf(tc[0], fminf(tc[1], tc[2]));
-    for (int k = 0; k < 3; k++) {
-        const int exit_voxel = f2i((fmaf(dir[k], texit, org[k]) - g->bbox_min[k]) * c->ginv[k]);
-        const int next = texit == tc[k] ? point[k] + (dir[k] >= 0.0f ? 0 : -1) : exit_voxel;
-        w->voxel[k] = dir[k] >= 0.0f ? imax(next, w->voxel[k]) : imin(next, w->voxel[k]);
-    }
-    w->texit = texit;
-    const int out = w->voxel[0] < 0 || w->voxel[0] >= c->dims[0] || w->voxel[1] < 0 || w->voxel[1] >= c->dims[1] ||
-                    w->voxel[2] < 0 || w->voxel[2] >= c->dims[2];
-    if (!test) return out;
-    w->cells++;
-    if (g->compressed) {
-        int cur = begin;
-        int ref = cur >= 0 ? g->refs[cur++] : -1;
-        while (ref >= 0) { intersect_tri(c->tris + ref, org, dir, c->ray->tmin, ref, &w->hit); ref = g->refs[cur++]; }
-        w->steps += 1 + (cur - begin);
-    } else {
-        for (int cur = begin; cur < end; cur++) intersect_tri(c->tris + g->refs[cur], org, dir, c->ray->tmin, g->refs[cur], &w->hit);
-        w->steps += 1 + (end - begin);
-    }
-    return w->hit.t <= texit || out;
-}
-
-#define OG_MAX_SEGMENTS 32
-
-void og_traverse_split(const og_grid* g, const og_tri* tris, const og_ray* rays, og_hit* hits, int num_rays, int mode,
-                       int step_limit, int voxels_per_segment, int* stats) {
-    og_init();
-    for (int i = 0; i < num_rays; i++) {
-        const og_ray* ray = rays + i;
-        og_ctx c; ctx_init(&c, g, tris, ray);
-        float t0[3], t1[3];
-        for (int k = 0; k < 3; k++) {
-            const float a = (g->bbox_min[k] - ray->org[k]) * c.inv[k], b = (g->bbox_max[k] - ray->org[k]) * c.inv[k];
-            t0[k] = sel_min(a, b); t1[k] = sel_max(a, b);
-        }
-        const float tstart = fmaxf(fmaxf(t0[0], fmaxf(t0[1], t0[2])), ray->tmin);
-        const float tend = fminf(fminf(t1[0], fminf(t1[1], t1[2])), ray->tmax);
-        og_walk w; memset(&w, 0, sizeof w);
-        w.hit.id = -1; w.hit.t = ray->tmax;
-        int serial_cells = 0, critical = 0, used = 1, started = 1;
-        if (!(tstart > tend)) {
-            voxel_at(&c, tstart, w.voxel);
-            int done = 0;
-            while (!done && w.steps < step_limit) done = walk_cell(&c, &w, 1);
-            critical = w.cells;
-            if (!done) {
-                /* the rest of the ray: [w.texit, tend] in `count` segments; segment 0 continues from the exact state */
-                float reach = 0.0f;                                  /* finest voxels crossed along the dominant axis */
-                for (int k = 0; k < 3; k++) reach = fmaxf(reach, fabsf(ray->dir[k]) * c.ginv[k]);
-                reach *= tend - w.texit;
-                int count = voxels_per_segment > 0 ? (int)(reach / (float)voxels_per_segment) + 1 : 1;
-                if (count > OG_MAX_SEGMENTS) count = OG_MAX_SEGMENTS;
-                if (!(count >= 1)) count = 1;
-                /* every segment records the states it passes (voxel after each cell, counters so far); a segment ends where its
-                 * state equals ANY recorded state of the next one that still carries the untouched hit (cells overlap after
-                 * expand_grid, so two walks of the same ray may need a few cells before they fall into step) */
-                enum { kHist = 512 };
-                typedef struct { int voxel[3]; int steps, cells, clean; } og_mark;
-                static __thread og_mark* marks = NULL;
-                if (!marks) marks = (og_mark*)malloc(sizeof(og_mark) * kHist * OG_MAX_SEGMENTS);
-                og_walk seg[OG_MAX_SEGMENTS]; int num_marks[OG_MAX_SEGMENTS]; int state[OG_MAX_SEGMENTS];  /* 0 joined, 1 ended */
-                int join_at[OG_MAX_SEGMENTS], walked[OG_MAX_SEGMENTS];
-                const og_hit hit0 = w.hit;
-                for (int s = count - 1; s >= 0; s--) {
-                    og_walk* q = &seg[s];
-                    og_mark* mine = marks + (size_t)s * kHist;
-                    const og_mark* next = marks + (size_t)(s + 1) * kHist;
-                    memset(q, 0, sizeof(og_walk));
-                    q->hit = hit0;
-                    num_marks[s] = 0; state[s] = 1; join_at[s] = -1;
-                    if (s == 0) memcpy(q->voxel, w.voxel, sizeof w.voxel);
-                    else {
-                        const float ts = w.texit + (tend - w.texit) * ((float)s / (float)count);
-                        voxel_at(&c, ts, q->voxel);
-                        walk_cell(&c, q, 0);                         /* untested first cell: fixes a start state */
-                    }
-                    const int started_outside = q->voxel[0] < 0 || q->voxel[0] >= c.dims[0] || q->voxel[1] < 0 || q->voxel[1] >= c.dims[1] ||
-                                                q->voxel[2] < 0 || q->voxel[2] >= c.dims[2];
-                    if (!started_outside) {
-                        for (;;) {
-                            /* the state before the next cell */
-                            const int clean = q->hit.id == hit0.id && q->hit.t == hit0.t;
-                            if (num_marks[s] < kHist) {
-                                og_mark* m = mine + num_marks[s]++;
-                                memcpy(m->voxel, q->voxel, sizeof q->voxel); m->steps = q->steps; m->cells = q->cells; m->clean = clean;
-                            }
-                            if (clean && s + 1 < count) {
-                                int found = -1;
-                                for (int k = 0; k < num_marks[s + 1] && found < 0; k++)
-                                    if (next[k].clean && next[k].voxel[0] == q->voxel[0] && next[k].voxel[1] == q->voxel[1] && next[k].voxel[2] == q->voxel[2]) found = k;
-                                if (found >= 0) { state[s] = 0; join_at[s] = found; break; }
-                            }
-                            if (walk_cell(&c, q, 1)) break;
-                        }
-                    }
-                    walked[s] = q->cells;
-                }
-                /* the chain: from segment 0, enter segment s+1 at mark join_at[s]; what s+1 did before that mark is dropped */
-                int longest = 0, s = 0, skip_steps = 0, skip_cells = 0, entered = 0, deepest = 0;
-                for (;; s++) {
-                    if (!state[s] && join_at[s] >= 0) {
-                        w.steps += seg[s].steps - skip_steps; w.cells += seg[s].cells - skip_cells;
-                        const og_mark* m = marks + (size_t)(s + 1) * kHist + join_at[s];
-                        /* segment s+1 must still have been running at that mark: true by construction (marks are states it left from) */
-                        skip_steps = m->steps; skip_cells = m->cells; entered = join_at[s];
-                        if (entered > deepest) deepest = entered;
-                        /* if s+1 itself joined s+2 before the mark we entered at, the rest of the chain is unusable: cannot happen,
-                         * marks end where the segment ended */
-                        continue;
-                    }
-                    w.steps += seg[s].steps - skip_steps; w.cells += seg[s].cells - skip_cells;
-                    break;
-                }
-                (void)entered;
-                w.hit = seg[s].hit;
-                used = s + 1;
-                for (int k = 0; k < count; k++)
-                    if (walked[k] > longest) longest = walked[k];
-                critical += longest;
-                started = count | (deepest << 8);
-            }
-            serial_cells = w.cells;
-        }
-        if (mode != 1) w.hit.id = w.steps;
-        hits[i] = w.hit;
-        if (stats) { stats[4 * i] = serial_cells; stats[4 * i + 1] = critical; stats[4 * i + 2] = used; stats[4 * i + 3] = started; }
-    }
-}

@@ -59,7 +59,6 @@ def dll():
                                         C.c_uint32, C.c_void_p]
         _dll.og_traverse_record.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _dll.og_traverse_record_cells.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
-        _dll.og_traverse_split.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     return _dll
 
 
@@ -116,16 +115,6 @@ class Grid:
         hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
         dll().og_traverse(self.ptr, tris.ctypes.data, rays.ctypes.data, hits.ctypes.data, rays.shape[0], mode, threads)
         return hits
-
-    def traverse_split(self, tris: np.ndarray, rays: np.ndarray, mode: int = 1, step_limit: int = 64, voxels_per_segment: int = 32):
-        """Model of hagrid_b200's straggler path (og_traverse_split): hits + per-ray statistics
-        [serial cells, critical-path cells, segments in the chain, segments started]."""
-        tris = np.ascontiguousarray(tris); rays = np.ascontiguousarray(rays)
-        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
-        stats = np.zeros((rays.shape[0], 4), dtype=np.int32)
-        dll().og_traverse_split(self.ptr, tris.ctypes.data, rays.ctypes.data, hits.ctypes.data, rays.shape[0], mode,
-                                step_limit, voxels_per_segment, stats.ctypes.data)
-        return hits, stats
 
     def record(self, tris: np.ndarray, rays: np.ndarray, max_steps: int = 128) -> np.ndarray:
         """Statistics: (num_rays, max_steps) int16, reference count of each visited cell, -1 padded."""
