@@ -805,6 +805,9 @@ std::atomic<int> g_variant{-1};
 std::atomic<int> g_host_frame_chunk{256 * 1024};
 // trace_two_waves: chunks a frame is cut into (their chains alternate between two streams)
 std::atomic<int> g_two_wave_chunks{1};
+// incoherent buffers smaller than this many rays are traced one thread per ray: the persistent voting warps pay off from
+// about 600 K rays (tools/gpu_incoherent_threshold.py: 259 K rays of the C5 second wave 0.363 vs 0.432 ms, 1 M rays 0.785 vs 0.722)
+std::atomic<int> g_vote_min_rays{768 << 10};
 // rasters smaller than this many rays are traced one thread per ray (re-tiled): a small launch does not fill the resident warps
 std::atomic<int> g_tile_min_rays{1280 << 10};      // profiles/r02_traverse_experiments.md: half a 1920x1080 frame is on the line
 
@@ -927,7 +930,7 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
         buf = classify_buffer(st, rays, num_rays);
         if (variant == 3) {
             // small buffers do not fill the resident-warp kernels (7 104 warps on 148 SMs): one thread per ray then
-            if (buf->cls == 0) variant = num_rays < (128 << 10) ? 0 : 1;
+            if (buf->cls == 0) variant = num_rays < g_vote_min_rays.load() ? 0 : 1;
             else               variant = num_rays < g_tile_min_rays.load() ? 2 : 4;
         }
         if (variant == 4 && buf->cls > 0) {
@@ -1066,7 +1069,9 @@ void launch_host_frame(const Grid& grid, const CellT* cells, const Tri* tris, co
         HGB_CUDA(cudaEventRecord(st.uploaded[c], up));
         stamp(up);
         HGB_CUDA(cudaStreamWaitEvent(run, st.uploaded[c], 0));
-        enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, dev_hits + begin, count, variant, nullptr, width,
+        // an incoherent chunk below the voting kernel's break-even size is traced one thread per ray
+        const int chunk_variant = traverse_variant() == 3 && variant == 1 && count < g_vote_min_rays.load() ? 0 : variant;
+        enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, dev_hits + begin, count, chunk_variant, nullptr, width,
                                 st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
         stamp(run);
         HGB_CUDA(cudaEventRecord(st.traced[c], run));
@@ -1114,7 +1119,7 @@ void launch_to_host(const Grid& grid, const CellT* cells, const Tri* tris, const
         cudaStream_t run = st.streams[2 + (c & 1)];
         // second-wave rays are incoherent by construction: no look at their layout
         int variant = traverse_variant();
-        if (variant == 3) variant = count < (128 << 10) ? 0 : 1;
+        if (variant == 3) variant = count < g_vote_min_rays.load() ? 0 : 1;
         else if (variant != 1) variant = 0;
         enqueue<CellT, kPrimId>(grid, cells, tris, dev_rays + begin, dev_hits + begin, count, variant, nullptr, 0,
                                 st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
@@ -1157,8 +1162,8 @@ void launch_two_waves(const Grid& grid, const CellT* cells, const Tri* tris, int
         cudaStream_t run = st.streams[2 + (c & 1)];
         int first = forced, second = forced;
         if (forced == 3) {
-            first = width > 0 ? (count < g_tile_min_rays.load() ? 2 : 4) : (count < (128 << 10) ? 0 : 1);
-            second = count < (128 << 10) ? 0 : 1;
+            first = width > 0 ? (count < g_tile_min_rays.load() ? 2 : 4) : (count < g_vote_min_rays.load() ? 0 : 1);
+            second = count < g_vote_min_rays.load() ? 0 : 1;
         } else if (forced == 2 || forced == 4) {
             if (width <= 0) first = 0;
             second = 0;
@@ -1257,6 +1262,7 @@ bool set_traversal_option(const char* key, int value) {
     if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk.store(value > 0 ? value : 256 * 1024); return true; }
     if (!std::strcmp(key, "ray_sort")) { g_ray_sort.store(value != 0); return true; }
     if (!std::strcmp(key, "two_wave_chunks")) { g_two_wave_chunks.store(value > 0 ? min(value, 16) : 1); return true; }
+    if (!std::strcmp(key, "vote_min_rays")) { g_vote_min_rays.store(value >= 0 ? value : (768 << 10)); return true; }
     if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (1280 << 10)); return true; }
     return false;
 }
