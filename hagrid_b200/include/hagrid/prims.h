@@ -3,4 +3,5 @@
 #ifndef PRIMITIVES_H
 #define PRIMITIVES_H
 #include "hgb_types.h"
+#include "hgb_inline.h"     // lookup_entry, foreach_ref, intersect_prim_ray, load_ray, ... (the reference's inline helpers)
 #endif
