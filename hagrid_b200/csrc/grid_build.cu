@@ -284,11 +284,54 @@ constexpr int kKeptCode = 0x100;
 
 /// Per reference: kept (its cell is a leaf), dropped (filtered out) or the child
 /// mask of a splitting cell. code = kKeptCode | 0 | mask.
+///
+/// HGB_CLASSIFY_STAGED (build-time alternative, tools/gpu_build_variants.py): the north star's "cp.async staging of
+/// triangle and cell arrays into shared memory" for this kernel -- every thread requests its triangle (3 x 16 B) and
+/// its cell (2 x 16 B) with cp.async.ca into the block's shared memory as soon as it knows the two indices, all
+/// threads wait once (cp.async.wait_all), and the separating-axis tests read shared memory. Measured on the 2 M-triangle
+/// build (profiles/r02_build_staging.md): no faster than loading into registers -- the gathers are the same dependent
+/// 16-byte requests either way, what the kernel waits for is their latency, and the 10 KB of shared memory per block
+/// cost resident warps -- so the register form below is what ships.
+#ifdef HGB_CLASSIFY_STAGED
+__device__ __forceinline__ void stage16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(unsigned(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+#endif
+
 __global__ void __launch_bounds__(kBlock) classify_refs(const __grid_constant__ BuildParams P, const Tri* __restrict__ tris,
                                                         const int* __restrict__ ref_ids, const int* __restrict__ cell_ids,
                                                         const Cell* __restrict__ cells, const int* __restrict__ split,
                                                         int num_refs, int* __restrict__ codes) {
     const int id = blockIdx.x * kBlock + threadIdx.x;
+#ifdef HGB_CLASSIFY_STAGED
+    __shared__ float4 staged_tri[kBlock][3];
+    __shared__ int4 staged_cell[kBlock][2];
+    const int cell = id < num_refs ? cell_ids[id] : -1;
+    const bool splits = cell >= 0 && split[cell];
+    if (splits) {
+        const float4* t = reinterpret_cast<const float4*>(tris + ref_ids[id]);
+        const int4* c = reinterpret_cast<const int4*>(cells + cell);
+        stage16(&staged_tri[threadIdx.x][0], t); stage16(&staged_tri[threadIdx.x][1], t + 1); stage16(&staged_tri[threadIdx.x][2], t + 2);
+        stage16(&staged_cell[threadIdx.x][0], c); stage16(&staged_cell[threadIdx.x][1], c + 1);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (id >= num_refs) return;
+    int code = 0;
+    if (cell >= 0) {
+        if (!splits) code = kKeptCode;
+        else {
+            const float4 a = staged_tri[threadIdx.x][0], b = staged_tri[threadIdx.x][1], c = staged_tri[threadIdx.x][2];
+            dev::TriData t;
+            t.v0 = {a.x, a.y, a.z}; t.e1 = {b.x, b.y, b.z}; t.e2 = {c.x, c.y, c.z}; t.n = {a.w, b.w, c.w};
+            const int4 lo = staged_cell[threadIdx.x][0], hi = staged_cell[threadIdx.x][1];
+            dev::CellBox box;
+            box.min_x = lo.x; box.min_y = lo.y; box.min_z = lo.z; box.begin = lo.w;
+            box.max_x = hi.x; box.max_y = hi.y; box.max_z = hi.z; box.end = hi.w;
+            code = child_mask(P, t, box);
+        }
+    }
+    codes[id] = code;
+#else
     if (id >= num_refs) return;
     const int cell = cell_ids[id];
     int code = 0;
@@ -297,6 +340,7 @@ __global__ void __launch_bounds__(kBlock) classify_refs(const __grid_constant__ 
         else code = child_mask(P, dev::load_tri(tris, ref_ids[id]), dev::load_cell_box(cells, cell));
     }
     codes[id] = code;
+#endif
 }
 
 /// Packed counters of one reference: high word = 1 if kept, low word = number of children
