@@ -482,7 +482,7 @@ void build_grid(MemManager& mem, const Tri* tris, int num_tris, Grid& grid, floa
         unsigned lo = 0xFFFFFFFFu, hi = 0u;
         for (int k = 0; k < 3; k++) { init[k] = lo; init[3 + k] = hi; }
         HGB_CUDA(cudaMemcpyAsync(box_bits, init, sizeof(init), cudaMemcpyHostToDevice, 0));
-        scene_bounds<<<std::max(1, std::min(blocks_for(num_tris), 148 * 8)), kBlock>>>(tris, num_tris, box_bits); count_launch();
+        scene_bounds<<<std::max(1, std::min(blocks_for(num_tris), sm_count() * 8)), kBlock>>>(tris, num_tris, box_bits); count_launch();
     }
     unsigned box_host[6];
     HGB_CUDA(cudaMemcpy(box_host, box_bits, sizeof(box_host), cudaMemcpyDeviceToHost));

@@ -402,7 +402,7 @@ inline bool sort_pairs(int* keys, int* vals, int* keys_alt, int* vals_alt, int n
     unsigned* counters = hist + kSortMaxPasses * kRadix;                 // one tile counter per pass
     unsigned* status = counters + 8;                                     // tiles * 256
     HGB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int) * (size_t(kSortMaxPasses) * kRadix + 8 + size_t(tiles) * kRadix), 0));
-    radix_histograms<<<std::min(tiles, 148 * 8), kSortThreads>>>(keys, n, bits, hist); count_launch();
+    radix_histograms<<<std::min(tiles, sm_count() * 8), kSortThreads>>>(keys, n, bits, hist); count_launch();
     radix_digit_offsets<<<1, kRadix>>>(hist, passes); count_launch();
     bool in_alt = false;
     for (int p = 0; p < passes; p++) {

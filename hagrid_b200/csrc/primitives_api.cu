@@ -92,7 +92,7 @@ void prim_reduce(MemManager& mem, const void* in, int n, int op, void* out) {
     HGB_CUDA(cudaMemcpyAsync(acc, &identity[op], sizeof(unsigned), cudaMemcpyHostToDevice, 0));
     (void)mem;
     if (n > 0) {
-        const int blocks = std::min((n + 255) / 256, 148 * 8);
+        const int blocks = std::min((n + 255) / 256, sm_count() * 8);
         if (op == 0) reduce_kernel<0><<<blocks, 256>>>(in, n, acc);
         else if (op == 1) reduce_kernel<1><<<blocks, 256>>>(in, n, acc);
         else if (op == 2) reduce_kernel<2><<<blocks, 256>>>(in, n, acc);

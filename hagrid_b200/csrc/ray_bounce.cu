@@ -119,10 +119,7 @@ void generate_bounce_rays_on(cudaStream_t stream, const Tri* tris, int num_tris,
 
 void count_hits_on(cudaStream_t stream, const Hit* hits, int num_hits, unsigned long long* counters) {
     if (num_hits <= 0) return;
-    int sms = 0, dev = 0;
-    HGB_CUDA(cudaGetDevice(&dev));
-    HGB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int blocks = std::min((num_hits + 255) / 256, sms * 8);
+    const int blocks = std::min((num_hits + 255) / 256, sm_count() * 8);
     count_hits_kernel<<<blocks, 256, 0, stream>>>(hits, num_hits, counters); count_launch();
     HGB_CUDA(cudaGetLastError());
 }

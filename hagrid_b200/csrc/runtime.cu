@@ -103,6 +103,19 @@ void MemManager::debug_slots() const {
     std::cout << double(total) / (1024.0 * 1024.0) << "MB total" << std::endl;
 }
 
+int sm_count() {
+    static std::atomic<int> counts[64];
+    int dev = 0;
+    HGB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return 148;
+    int n = counts[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        HGB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        counts[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 /// Hands memory the stream-ordered pool retains back to the driver (after a scene has been destroyed)
 void trim_device_pool() {
     int dev = 0;

@@ -21,6 +21,9 @@ inline void check_cuda(cudaError_t err, const char* what, const char* file, int 
 extern std::atomic<unsigned long long> g_kernel_launches;
 inline void count_launch(int n = 1) { g_kernel_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
+/// Multiprocessors of the current device (queried once per device): grids of grid-stride kernels are sized by it
+int sm_count();
+
 struct Tri; struct Ray; struct Hit;
 /// Stream-taking forms of generate_bounce_rays / count_hits (hgb_api.h), used by the two-wave frame; without `keys` ray i's
 /// random stream is named first_key + i (a chunk of a buffer passes where it starts)
