@@ -30,7 +30,7 @@ long long file_size(std::FILE* fp) {
 
 constexpr char kGridMagic[8] = {'H', 'G', 'R', 'I', 'D', '0', '0', '1'};
 
-struct GridHeader {                 // little-endian, 128 bytes + offsets
+struct GridHeader {                 // little-endian, 104 bytes, followed by the offsets
     char    magic[8];
     float   bbox_min[3], bbox_max[3];
     int32_t dims[3];
@@ -148,19 +148,48 @@ bool load_grid(MemManager& mem, const std::string& path, Grid& grid, std::string
     std::vector<int> offsets(size_t(h.num_offsets));
     if (!f.read(offsets.data(), sizeof(int) * offsets.size())) { error = "read error"; return false; }
 
-    bool ok = true;
-    auto fetch = [&](size_t bytes) -> char* {
+    // Everything is read and checked on the host before anything is allocated: a file whose indices point outside its
+    // own arrays would send the traversal out of bounds (or round in circles through the voxel map)
+    long long top = 1;
+    for (int k = 0; k < 3; k++) {
+        if (h.dims[k] <= 0 || ((long long)h.dims[k] << h.shift) > (1ll << 30) || !(h.bbox_max[k] > h.bbox_min[k])) { error = "corrupt grid header"; return false; }
+        top *= h.dims[k];
+    }
+    if (top > h.num_entries || h.num_cells <= 0) { error = "corrupt grid header"; return false; }
+    for (size_t i = 0; i < offsets.size(); i++)
+        if (offsets[i] < 0 || offsets[i] > h.num_entries || (i > 0 && offsets[i] < offsets[i - 1])) { error = "corrupt grid file: level offsets"; return false; }
+    std::vector<uint32_t> host_entries(size_t(h.num_entries));
+    std::vector<char> host_cells(cell_bytes);
+    std::vector<int> host_refs(size_t(h.num_refs));
+    if (!f.read(host_entries.data(), 4 * host_entries.size()) || !f.read(host_cells.data(), cell_bytes) ||
+        !f.read(host_refs.data(), 4 * host_refs.size())) { error = "read error"; return false; }
+    for (size_t i = 0; i < host_entries.size(); i++) {
+        const uint32_t log_dim = host_entries[i] & 3u, begin = host_entries[i] >> 2;
+        // a leaf names a cell; an inner node names a block of (2^log_dim)^3 entries that lies behind it (levels only point down)
+        const bool ok_entry = log_dim == 0 ? begin < uint32_t(h.num_cells)
+                                           : begin > i && (unsigned long long)begin + (1ull << (3 * log_dim)) <= (unsigned long long)h.num_entries;
+        if (!ok_entry) { error = "corrupt grid file: voxel map"; return false; }
+    }
+    for (int c = 0; c < h.num_cells; c++) {
+        bool ok_cell;
+        if (h.compressed) {
+            const SmallCell& cell = reinterpret_cast<const SmallCell*>(host_cells.data())[c];
+            ok_cell = cell.begin >= -1 && cell.begin < h.num_refs;
+        } else {
+            const Cell& cell = reinterpret_cast<const Cell*>(host_cells.data())[c];
+            ok_cell = cell.begin >= 0 && cell.begin <= cell.end && cell.end <= h.num_refs;
+        }
+        if (!ok_cell) { error = "corrupt grid file: cells"; return false; }
+    }
+    if (h.compressed && h.num_refs > 0 && host_refs.back() >= 0) { error = "corrupt grid file: the last reference list has no sentinel"; return false; }
+    auto upload = [&](const void* host, size_t bytes) -> char* {
         char* dev = mem.alloc<char>(bytes ? bytes : 16);
-        if (!ok || bytes == 0) return dev;
-        std::vector<char> host(bytes);
-        ok = f.read(host.data(), bytes);
-        if (ok) mem.copy<Copy::HST_TO_DEV>(dev, host.data(), bytes);
+        if (bytes) mem.copy<Copy::HST_TO_DEV>(dev, static_cast<const char*>(host), bytes);
         return dev;
     };
-    char* entries = fetch(sizeof(Entry) * size_t(h.num_entries));
-    char* cells = fetch(cell_bytes);
-    char* refs = fetch(sizeof(int) * size_t(h.num_refs));
-    if (!ok) { mem.free(entries); mem.free(cells); mem.free(refs); error = "read error"; return false; }
+    char* entries = upload(host_entries.data(), 4 * host_entries.size());
+    char* cells = upload(host_cells.data(), cell_bytes);
+    char* refs = upload(host_refs.data(), 4 * host_refs.size());
     grid.entries = reinterpret_cast<Entry*>(entries);
     grid.cells = h.compressed ? nullptr : reinterpret_cast<Cell*>(cells);
     grid.small_cells = h.compressed ? reinterpret_cast<SmallCell*>(cells) : nullptr;

@@ -93,7 +93,10 @@ HGB_API int  hgb_scene_set_tris(hgb_scene* scene, const void* host_tris, int num
  * + fan triangulation + triangle setup. This library parses the file with `threads` host threads (0 = all) and
  * builds the 48-byte records on the device; the reference build of this ABI runs the reference's own
  * single-threaded load_model and uploads the result. Returns the number of triangles, negative on error
- * (unreadable file, or anything the reference's loader counts as an error). */
+ * (unreadable file, or anything the reference's loader counts as an error). Two inputs the reference mishandles are
+ * errors here: a position index beyond the file's vertices (the reference reads out of bounds) and a line of 1023
+ * characters or more, comments included (the reference's getline fails there and it silently keeps the geometry
+ * parsed so far, src/load_obj.cpp:103-105). */
 HGB_API int  hgb_scene_load_obj(hgb_scene* scene, const char* path, int threads);
 /* The host half of the ingest on its own (no device needed): positions (index 0 = the loader's dummy vertex,
  * src/load_obj.cpp:96) and three position indices per fan triangle, in file order. */

@@ -58,7 +58,16 @@ def test_grid_cache_round_trip(lib, tmp_path, compress):
     b.build_all(g.top_density, g.snd_density)             # the loaded arrays belong to the scene's pool: a rebuild frees them
     # damaged files are refused, the scene keeps its grid
     blob = path.read_bytes()
-    for bad in (blob[:-3], b"XGRID001" + blob[8:], blob + b"\0"):
+    header = 104 + 4 * len(ia.as_dict()["offsets"])
+    damaged = [blob[:-3], b"XGRID001" + blob[8:], blob + b"\0"]
+    # right size, wrong contents: a voxel-map word that names a cell that does not exist, an inner node that points at
+    # itself (an endless look-up), a cell whose reference range leaves the array
+    bad_leaf = bytearray(blob); bad_leaf[header:header + 4] = np.uint32(0x7FFFFFF << 2).tobytes()
+    self_loop = bytearray(blob); self_loop[header:header + 4] = np.uint32((0 << 2) | 1).tobytes()
+    cells_at = header + 4 * ia.num_entries
+    bad_cell = bytearray(blob); bad_cell[cells_at + 12:cells_at + 16] = np.int32(2**30).tobytes()
+    damaged += [bytes(bad_leaf), bytes(self_loop), bytes(bad_cell)]
+    for bad in damaged:
         (tmp_path / "bad.hgrid").write_bytes(bad)
         with pytest.raises(HagridError):
             b.load_grid(tmp_path / "bad.hgrid")
