@@ -390,7 +390,8 @@ inline size_t sort_scratch_ints(int n) { return size_t(kSortMaxPasses) * kRadix 
 
 /// Stable sort of (key, value) pairs on the low `bits` bits (at most 32 - 4 passes of 8) of the keys; n < 2^28.
 /// Ping-pongs between (keys, vals) and (keys_alt, vals_alt); returns true when the result ended in the *_alt buffers.
-inline bool sort_pairs(int* keys, int* vals, int* keys_alt, int* vals_alt, int n, int bits, int* scratch) {
+/// Enqueued on `stream` (the construction uses the legacy default stream).
+inline bool sort_pairs(int* keys, int* vals, int* keys_alt, int* vals_alt, int n, int bits, int* scratch, cudaStream_t stream = 0) {
     if (n <= 0 || bits <= 0) return false;
     if (n >= (1 << kSortValueBits) || bits > kSortMaxPasses * kRadixBits) {
         std::fprintf(stderr, "hagrid_b200: sort_pairs handles fewer than 2^28 pairs and at most 32 key bits\n");
@@ -401,14 +402,14 @@ inline bool sort_pairs(int* keys, int* vals, int* keys_alt, int* vals_alt, int n
     unsigned* hist = reinterpret_cast<unsigned*>(scratch);               // kSortMaxPasses * 256
     unsigned* counters = hist + kSortMaxPasses * kRadix;                 // one tile counter per pass
     unsigned* status = counters + 8;                                     // tiles * 256
-    HGB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int) * (size_t(kSortMaxPasses) * kRadix + 8 + size_t(tiles) * kRadix), 0));
-    radix_histograms<<<std::min(tiles, sm_count() * 8), kSortThreads>>>(keys, n, bits, hist); count_launch();
-    radix_digit_offsets<<<1, kRadix>>>(hist, passes); count_launch();
+    HGB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int) * (size_t(kSortMaxPasses) * kRadix + 8 + size_t(tiles) * kRadix), stream));
+    radix_histograms<<<std::min(tiles, sm_count() * 8), kSortThreads, 0, stream>>>(keys, n, bits, hist); count_launch();
+    radix_digit_offsets<<<1, kRadix, 0, stream>>>(hist, passes); count_launch();
     bool in_alt = false;
     for (int p = 0; p < passes; p++) {
         int* kin = in_alt ? keys_alt : keys;   int* vin = in_alt ? vals_alt : vals;
         int* kout = in_alt ? keys : keys_alt;  int* vout = in_alt ? vals : vals_alt;
-        radix_onesweep<<<tiles, kSortThreads>>>(kin, vin, kout, vout, n, p * kRadixBits, std::min(kRadixBits, bits - p * kRadixBits),
+        radix_onesweep<<<tiles, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, p * kRadixBits, std::min(kRadixBits, bits - p * kRadixBits),
                                                 hist + p * kRadix, status, counters + p, unsigned(p)); count_launch();
         in_alt = !in_alt;
     }

@@ -435,14 +435,34 @@ __device__ long long g_tile_trace[3 * 8192];
 __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
-template <typename CellT, bool kPrimId>
+/// Longest tiles first, the very longest in parts. A launch ends with a tail: the queue is empty, every warp finishes
+/// the tile it holds, and the launch lasts until the slowest of them is done (C2: queue dry at 139 us, last warp back
+/// at 160-165 us; C5: dry at 65 us, last warp at 210 us -- tiles of foliage whose rays diverge and take turns). Callers
+/// trace the same buffer again and again (a viewer's frame loop, a benchmark's iterations) and a frame resembles the
+/// one before, so a launch can time its tiles (`cost`: clock ticks / 64, one 2-byte store per tile) and later launches
+/// on the same buffer are handed a ticket list made from those times on a side stream (order_tiles): tiles by cost
+/// class, longest first, so that the tiles in flight when the queue runs dry are the cheap ones; and the few tiles
+/// that alone last a good part of the whole launch as 2^split_log tickets each, every ticket tracing 32 >> split_log
+/// of the tile's rays -- where the lanes of a warp take turns, fewer lanes per warp make a shorter chain. A ticket is
+/// tile | (part + 1) << 26 (part bits 0: the whole tile; at most 32 parts, so never all ones) or -1 (nothing: the list
+/// has a fixed length the host knows).
+/// Every ray is traced exactly once whatever the list says, each in its own lane with its own state: the list cannot
+/// change a hit.
+struct TileHistory {
+    const int* tickets;          // null: tile k is ticket k
+    unsigned short* cost;        // written by the kTimed instantiation only (such a launch gets a list without parts)
+    int extra_tickets;           // length of the list - number of tiles
+    int split_log;
+};
+
+template <typename CellT, bool kPrimId, bool kTimed = false>
 __global__ void __launch_bounds__(kTileBlock, kTileBlocksPerSm)
 traverse_tiles(const __grid_constant__ TraversalParams P,
                const uint32_t* __restrict__ entries, const CellT* __restrict__ cells,
                const int* __restrict__ ref_ids, const Tri* __restrict__ tris,
                const Ray* __restrict__ rays, Hit* __restrict__ hits, int num_rays,
                const int* __restrict__ layout, int host_width, unsigned* __restrict__ next_tile, unsigned ticket_base,
-               int* __restrict__ feedback) {
+               int* __restrict__ feedback, const __grid_constant__ TileHistory history) {
     const int lane = threadIdx.x & 31;
     // feedback (device memory, may be null): [0] += warps whose rays did not share a direction octant, [1] += 1
     // per launch. A buffer of camera rays has a few such warps along the image axes; a buffer whose warps are
@@ -457,13 +477,18 @@ traverse_tiles(const __grid_constant__ TraversalParams P,
     int traced_tiles = 0;
     if (lane == 0 && trace_slot < 8192) g_tile_trace[3 * trace_slot] = global_ns();
 #endif
-    int tile = blockIdx.x * (kTileBlock / 32) + (threadIdx.x >> 5);
-    while (tile < num_tiles) {
+    const int num_tickets = num_tiles + history.extra_tickets;
+    int ticket = blockIdx.x * (kTileBlock / 32) + (threadIdx.x >> 5);
+    while (ticket < num_tickets) {
+        const int what = history.tickets ? __ldg(history.tickets + ticket) : ticket;
+        if (what == -1) { ticket = fetch_tile(next_tile, ticket_base, first_dynamic, lane); continue; }
+        const unsigned started = kTimed ? unsigned(clock()) : 0u;
         RayState r;
         bool ok = false;
         {
+            const int tile = what & ((1 << 26) - 1), part = int(unsigned(what) >> 26);
             int id = tile * 32 + lane;
-            if (id < num_rays) {
+            if (id < num_rays && (part == 0 || (lane >> (5 - history.split_log)) == part - 1)) {
                 if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
                 ok = start_ray(r, P, rays, id);
             }
@@ -471,19 +496,65 @@ traverse_tiles(const __grid_constant__ TraversalParams P,
         const bool uniform = walk_warp(ok, r, P, entries, cells, ref_ids, tris);
         if (!uniform && feedback && lane == 0) atomicAdd(feedback, 1);
         {   // the ray's place in the buffer again (cheaper than keeping it in a register across the march)
+            const int tile = what & ((1 << 26) - 1), part = int(unsigned(what) >> 26);
             int id = tile * 32 + lane;
-            if (id < num_rays) {
+            if (id < num_rays && (part == 0 || (lane >> (5 - history.split_log)) == part - 1)) {
                 if (width > 0) id = tiled_ray_index_nodiv(tile, lane, width);
                 finish_ray<kPrimId>(r, hits, id);
             }
         }
         __syncwarp();
+        if (kTimed && lane == 0) history.cost[what & ((1 << 26) - 1)] = (unsigned short)min((unsigned(clock()) - started) >> 6, 0xFFFFu);
 #ifdef HGB_TILE_TRACE
         traced_tiles++;
         if (lane == 0 && trace_slot < 8192) { g_tile_trace[3 * trace_slot + 1] = global_ns(); g_tile_trace[3 * trace_slot + 2] = traced_tiles; }
 #endif
-        tile = fetch_tile(next_tile, ticket_base, first_dynamic, lane);
+        ticket = fetch_tile(next_tile, ticket_base, first_dynamic, lane);
     }
+}
+
+/// stats[0] = the largest cost, stats[1] = the sum of all costs >> 8 (one block)
+__global__ void __launch_bounds__(1024) tile_cost_stats(const unsigned short* __restrict__ cost, int num_tiles, unsigned* __restrict__ stats) {
+    __shared__ unsigned warp_max[32];
+    __shared__ unsigned long long warp_sum[32];
+    unsigned m = 0;
+    unsigned long long sum = 0;
+    for (int t = threadIdx.x; t < num_tiles; t += 1024) { const unsigned c = cost[t]; m = max(m, c); sum += c; }
+    for (int d = 16; d > 0; d >>= 1) { m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, d)); sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d); }
+    if ((threadIdx.x & 31) == 0) { warp_max[threadIdx.x >> 5] = m; warp_sum[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = warp_max[threadIdx.x]; sum = warp_sum[threadIdx.x];
+        for (int d = 16; d > 0; d >>= 1) { m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, d)); sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d); }
+        if (threadIdx.x == 0) { stats[0] = m; stats[1] = unsigned(sum >> 8); }
+    }
+}
+
+/// keys[t] = the tile's cost class out of 2^bits equal classes between 0 and the largest cost, most expensive class
+/// first (the sort is stable: tiles of one class keep their buffer order and with it the cells they share with their
+/// neighbours); order[t] = t
+__global__ void __launch_bounds__(256) tile_order_keys(const unsigned short* __restrict__ cost, int num_tiles, int bits, const unsigned* __restrict__ stats,
+                                                       int* __restrict__ keys, int* __restrict__ order) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= num_tiles) return;
+    const unsigned top = __ldg(stats);
+    keys[t] = int(((top - unsigned(cost[t])) << bits) / (top + 1u));
+    order[t] = t;
+}
+
+/// The ticket list (TileHistory) from the sorted tiles: the first `split` of them get 2^split_log tickets each -- the
+/// parts of the tile if it alone costs `share` percent or more of what one of the launch's `warps` warps has to do
+/// (sum of all costs / warps), otherwise the whole tile and empty tickets -- the others one ticket each.
+__global__ void __launch_bounds__(256) tile_tickets(const int* __restrict__ sorted, const unsigned short* __restrict__ cost, const unsigned* __restrict__ stats,
+                                                    int num_tiles, int split, int split_log, int share, int warps, int* __restrict__ tickets) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int parts = 1 << split_log;
+    if (j >= num_tiles + split * (parts - 1)) return;
+    if (j >= split * parts) { tickets[j] = sorted[j - split * (parts - 1)]; return; }
+    const int tile = sorted[j >> split_log], part = j & (parts - 1);
+    // cost >= share % of sum / warps, the sum being kept >> 8
+    const bool in_parts = (unsigned long long)cost[tile] * unsigned(warps) * 100ull >= ((unsigned long long)stats[1] << 8) * unsigned(share);
+    tickets[j] = in_parts ? tile | ((part + 1) << 26) : part == 0 ? tile : -1;
 }
 
 // ---------------------------------------------------------------------------
@@ -735,7 +806,26 @@ struct DeviceState {
         int  feedback_mixed = 0, feedback_launches = 0;   // counter values when the buffer was armed
         bool feedback_armed = false;
         unsigned long long used = 0; // launch number of the last use (least recently used entry is replaced)
+        // tile history of a raster buffer (TileHistory): two cost arrays written alternately by the launches, the order
+        // made from the older one on the side stream, and the event that says the order is complete
+        int* history = nullptr;      // one allocation: the arrays below
+        int history_tiles = 0;       // tiles the allocation is good for
+        int* tickets[2] = {};        // ticket lists, tiles + kMaxSplitExtra each
+        int* sorted = nullptr;       // the tiles by cost class as the last sort left them (the list of a timed launch)
+        int* sort_space = nullptr;   // keys and values of the sort, twice, and its scratch
+        unsigned* stats = nullptr;
+        unsigned short* cost = nullptr;
+        int tile_launches = 0;       // launches of traverse_tiles on this buffer
+        int history_epoch = 0;
+        int pending_since = 0;       // the timed launch the pending order comes from
+        int order_ready = -1;        // index of the order array a launch may use (-1: none yet)
+        int order_pending = -1;      // index of the order array being made on the side stream (-1: none)
+        int extra[2] = {};           // tickets beyond one per tile in each list
+        int split_log[2] = {};
+        cudaEvent_t timed = nullptr, ordered = nullptr;
     };
+    static constexpr int kMaxSplit = 1024, kMaxSplitExtra = kMaxSplit * 31;
+    cudaStream_t side = nullptr;     // stream the orders are made on
     static constexpr int kSeenBuffers = 4;
     SeenBuffer seen[kSeenBuffers];
     unsigned long long launches = 0;
@@ -840,20 +930,105 @@ __global__ void __launch_bounds__(256) ray_bin_keys(const __grid_constant__ Trav
 
 std::atomic<int> g_ray_sort{0};
 
+// "tile_order": cost classes (bits, 1 ... 8) the tiles of a raster are handed out by; 0 = always buffer order
+std::atomic<int> g_tile_order_bits{8};
+// "tile_split" / "tile_split_log": how many of the most expensive tiles are handed out in 2^tile_split_log parts
+std::atomic<int> g_tile_split{256}, g_tile_split_log{2}, g_tile_split_share{50};
+std::atomic<int> g_tile_history_epoch{0};      // bumped when one of the three changes: what was learnt under other settings is dropped
+
+/// What the next launch of traverse_tiles on `buf` gets (TileHistory): the newest order -- the one made from timed
+/// launch k is used from launch k + 2 on, so that it is made while launch k + 1 runs and nobody waits for it -- and a
+/// cost array when this launch is one of those that time their tiles: the first ones on a buffer, later every 16th,
+/// and never while an order is still being made from the previous timing. Returns whether the launch is timed.
+bool tile_history(DeviceState& st, DeviceState::SeenBuffer& buf, int num_rays, TileHistory& history, cudaStream_t stream) {
+    const int tiles = (num_rays + 31) / 32;
+    if (!st.side) HGB_CUDA(cudaStreamCreateWithFlags(&st.side, cudaStreamNonBlocking));
+    if (buf.history_tiles < tiles) {
+        if (buf.order_pending >= 0) HGB_CUDA(cudaEventSynchronize(buf.ordered));
+        if (buf.history) { HGB_CUDA(cudaDeviceSynchronize()); HGB_CUDA(cudaFree(buf.history)); }
+        const size_t list = size_t(tiles) + DeviceState::kMaxSplitExtra;
+        const size_t ints = 2 * list + 4 * size_t(tiles) + prim::sort_scratch_ints(tiles) + 2;
+        HGB_CUDA(cudaMalloc(&buf.history, ints * sizeof(int) + size_t(tiles) * sizeof(unsigned short)));
+        buf.tickets[0] = buf.history; buf.tickets[1] = buf.history + list;
+        buf.sort_space = buf.history + 2 * list;
+        buf.stats = reinterpret_cast<unsigned*>(buf.history + ints - 2);
+        buf.cost = reinterpret_cast<unsigned short*>(buf.history + ints);
+        buf.sorted = nullptr;
+        buf.history_tiles = tiles;
+        buf.order_ready = buf.order_pending = -1; buf.tile_launches = 0;
+        if (!buf.timed) {
+            HGB_CUDA(cudaEventCreateWithFlags(&buf.timed, cudaEventDisableTiming));
+            HGB_CUDA(cudaEventCreateWithFlags(&buf.ordered, cudaEventDisableTiming));
+        }
+    }
+    if (buf.history_epoch != g_tile_history_epoch.load()) {
+        if (buf.order_pending >= 0) HGB_CUDA(cudaEventSynchronize(buf.ordered));
+        buf.history_epoch = g_tile_history_epoch.load();
+        buf.order_ready = buf.order_pending = -1; buf.tile_launches = 0;
+    }
+    const int k = buf.tile_launches++;
+    if (buf.order_pending >= 0 && k >= buf.pending_since + 2) {
+        // made during the launch before this one; the wait is a formality unless the device was idle in between
+        HGB_CUDA(cudaStreamWaitEvent(stream, buf.ordered, 0));
+        buf.order_ready = buf.order_pending;
+        buf.order_pending = -1;
+    }
+    const bool timed = buf.order_pending < 0 && (k < 4 || (k & 15) == 0);
+    if (timed) buf.pending_since = k;
+    history.cost = timed ? buf.cost : nullptr;
+    if (buf.order_ready >= 0 && !timed) {
+        history.tickets = buf.tickets[buf.order_ready];
+        history.extra_tickets = buf.extra[buf.order_ready];
+        history.split_log = buf.split_log[buf.order_ready];
+    } else if (buf.order_ready >= 0) {
+        history.tickets = buf.sorted;        // whole tiles: a part's time says nothing about its tile
+    }
+    return timed;
+}
+
+/// After a timed launch on `stream`: the ticket list for later launches, made on the side stream from the costs that
+/// launch leaves behind, into the list no launch is reading. (Launches of one buffer are ordered among themselves: on
+/// the legacy default stream, or on streams that start behind it and are joined back into it, launch_two_waves.)
+void order_tiles(DeviceState& st, DeviceState::SeenBuffer& buf, int num_rays, int bits, cudaStream_t stream) {
+    const int tiles = (num_rays + 31) / 32;
+    const int target = buf.order_ready == 0 ? 1 : 0;
+    int* keys = buf.sort_space; int* vals = keys + tiles; int* keys_alt = vals + tiles; int* vals_alt = keys_alt + tiles;
+    int* scratch = vals_alt + tiles;
+    const int split_log = std::max(0, std::min(5, g_tile_split_log.load()));
+    const int split = split_log ? std::min(std::min(tiles, g_tile_split.load()), DeviceState::kMaxSplit) : 0;
+    const int extra = split * ((1 << split_log) - 1);
+    const int warps = std::min(st.num_sms * kTileBlocksPerSm, round_div(tiles * 32, kTileBlock)) * (kTileBlock / 32);
+    HGB_CUDA(cudaEventRecord(buf.timed, stream));
+    HGB_CUDA(cudaStreamWaitEvent(st.side, buf.timed, 0));
+    tile_cost_stats<<<1, 1024, 0, st.side>>>(buf.cost, tiles, buf.stats); count_launch();
+    tile_order_keys<<<round_div(tiles, 256), 256, 0, st.side>>>(buf.cost, tiles, bits, buf.stats, keys, vals); count_launch();
+    buf.sorted = prim::sort_pairs(keys, vals, keys_alt, vals_alt, tiles, bits, scratch, st.side) ? vals_alt : vals;
+    tile_tickets<<<round_div(tiles + extra, 256), 256, 0, st.side>>>(buf.sorted, buf.cost, buf.stats, tiles, split, split_log,
+                                                                      g_tile_split_share.load(), warps, buf.tickets[target]); count_launch();
+    HGB_CUDA(cudaEventRecord(buf.ordered, st.side));
+    buf.order_pending = target;
+    buf.extra[target] = extra; buf.split_log[target] = split_log;
+}
+
 /// Enqueues one traversal launch on `stream`: 1 = persistent voting warps (needs `vote_counter`), 4 = resident
 /// warps pulling tiles (needs `ticket`), otherwise one thread per ray; 2 and 4 re-tile by the raster width in
 /// `layout[0]` (device) or `host_width`.
 template <typename CellT, bool kPrimId>
 void enqueue(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* rays, Hit* hits, int num_rays,
              int variant, const int* layout, int host_width, int* vote_counter, Ticket& ticket, int num_sms, cudaStream_t stream,
-             int* feedback = nullptr, const int* order = nullptr) {
+             int* feedback = nullptr, const int* order = nullptr, TileHistory history = TileHistory{nullptr, nullptr, 0, 0}) {
     auto entries = reinterpret_cast<const uint32_t*>(grid.entries);
     const TraversalParams P = params_of(grid);
     if (variant == 4) {
         const int blocks = min(num_sms * kTileBlocksPerSm, round_div(num_rays, kTileBlock));
-        traverse_tiles<CellT, kPrimId><<<blocks, kTileBlock, 0, stream>>>(
-            P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback);
-        ticket.base += unsigned((num_rays + 31) >> 5);      // one fetch per traced tile (fetch_tile)
+        if (history.cost)
+            traverse_tiles<CellT, kPrimId, true><<<blocks, kTileBlock, 0, stream>>>(
+                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback, history);
+        else
+            traverse_tiles<CellT, kPrimId, false><<<blocks, kTileBlock, 0, stream>>>(
+                P, entries, cells, grid.ref_ids, tris, rays, hits, num_rays, layout, host_width, ticket.word, ticket.base, feedback, history);
+        // one fetch per ticket (fetch_tile)
+        ticket.base += unsigned((num_rays + 31) >> 5) + unsigned(history.extra_tickets);
         count_launch();
     } else if (variant == 1) {
         HGB_CUDA(cudaMemsetAsync(vote_counter, 0, sizeof(int), stream));
@@ -884,6 +1059,9 @@ DeviceState::SeenBuffer* classify_buffer(DeviceState& st, const Ray* rays, int n
         for (auto& e : st.seen)
             if (e.used < buf->used) buf = &e;
         buf->cls = -1; buf->feedback_armed = false;
+        // what was learnt about another buffer's tiles says nothing about this one (a list still being made for it is
+        // made for nobody: the side stream finishes it before it starts the next)
+        buf->tile_launches = 0; buf->order_ready = buf->order_pending = -1;
     }
     buf->used = st.launches;
     volatile int* answer = buf->host;
@@ -961,8 +1139,13 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
         while ((1 << bits) < cells_top) bits++;
         order = prim::sort_pairs(keys, idx, keys_alt, idx_alt, num_rays, bits, idx_alt + num_rays) ? idx_alt : idx;
     }
+    TileHistory history{nullptr, nullptr, 0, 0};
+    bool timed = false;
+    const int order_bits = g_tile_order_bits.load();
+    if (variant == 4 && buf && buf->cls > 0 && order_bits > 0) timed = tile_history(st, *buf, num_rays, history, 0);
     enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, tiled && buf ? buf->layout : nullptr, 0,
-                            st.vote_counter, st.tiles, st.num_sms, 0, feedback, order);
+                            st.vote_counter, st.tiles, st.num_sms, 0, feedback, order, history);
+    if (timed) order_tiles(st, *buf, num_rays, order_bits, 0);
     if (feedback) {
         // copied back after launches 1, 2, 4 and then every 8th: one 8-byte copy in eight launches
         const int tick = ++buf->feedback_tick;
@@ -1150,7 +1333,8 @@ void launch_two_waves(const Grid& grid, const CellT* cells, const Tri* tris, int
     prepare_streams(st);
     int forced = traverse_variant();
     int width = 0;
-    if (forced >= 2 && forced <= 4) width = std::max(0, classify_buffer(st, rays, num_rays)->cls);
+    DeviceState::SeenBuffer* buf = nullptr;
+    if (forced >= 2 && forced <= 4) { buf = classify_buffer(st, rays, num_rays); width = std::max(0, buf->cls); }
     const int granule = width > 0 ? width * kTileH : kBlockThreads;
     const int chunks = std::max(1, std::min(g_two_wave_chunks.load(), num_rays / (256 << 10)));
     const long long step = ((long long)round_div(num_rays, chunks) + granule - 1) / granule * granule;
@@ -1168,8 +1352,13 @@ void launch_two_waves(const Grid& grid, const CellT* cells, const Tri* tris, int
             if (width <= 0) first = 0;
             second = 0;
         }
+        // a frame traced in one piece has its tiles handed out by what the frames before it cost (TileHistory)
+        TileHistory history{nullptr, nullptr, 0, 0};
+        const int order_bits = g_tile_order_bits.load();
+        const bool timed = first == 4 && count == num_rays && buf && width > 0 && order_bits > 0 && tile_history(st, *buf, count, history, run);
         enqueue<CellT, true>(grid, cells, tris, rays + begin, hits_primary + begin, count, first, nullptr, width,
-                             st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run);
+                             st.stream_vote_counters[c & 1], st.stream_tiles[c & 1], st.num_sms, run, nullptr, nullptr, history);
+        if (timed) order_tiles(st, *buf, count, order_bits, run);
         if (counters) count_hits_on(run, hits_primary + begin, count, counters);
         generate_bounce_rays_on(run, tris, num_tris, rays + begin, hits_primary + begin, count, offset, tmax, seed, bounce + begin,
                                 keys ? keys + begin : nullptr, int(begin));
@@ -1261,6 +1450,10 @@ bool set_traversal_option(const char* key, int value) {
     if (!std::strcmp(key, "traverse_variant")) { g_variant.store(value); return true; }
     if (!std::strcmp(key, "host_frame_chunk_rays")) { g_host_frame_chunk.store(value > 0 ? value : 256 * 1024); return true; }
     if (!std::strcmp(key, "ray_sort")) { g_ray_sort.store(value != 0); return true; }
+    if (!std::strcmp(key, "tile_order")) { g_tile_order_bits.store(std::max(0, std::min(12, value))); g_tile_history_epoch++; return true; }
+    if (!std::strcmp(key, "tile_split")) { g_tile_split.store(std::max(0, value)); g_tile_history_epoch++; return true; }
+    if (!std::strcmp(key, "tile_split_log")) { g_tile_split_log.store(value); g_tile_history_epoch++; return true; }
+    if (!std::strcmp(key, "tile_split_share")) { g_tile_split_share.store(std::max(0, value)); g_tile_history_epoch++; return true; }
     if (!std::strcmp(key, "two_wave_chunks")) { g_two_wave_chunks.store(value > 0 ? min(value, 16) : 1); return true; }
     if (!std::strcmp(key, "vote_min_rays")) { g_vote_min_rays.store(value >= 0 ? value : (768 << 10)); return true; }
     if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (1280 << 10)); return true; }
@@ -1306,7 +1499,26 @@ void traverse_grid_host(const Grid& grid, const Tri* tris, const Ray* host_rays,
     }
 }
 
+/// Diagnosis (tools/gpu_tile_costs.py): the tile times last recorded for the ray buffer (`rays`, `num_rays`), clock
+/// ticks / 64 per tile of 32 rays; returns the number of tiles copied (0: nothing recorded for that buffer).
+int debug_tile_costs(const void* rays, int num_rays, unsigned short* out, int capacity) {
+    DeviceState& st = device_state();
+    std::lock_guard<std::mutex> guard(st.lock);
+    for (auto& e : st.seen)
+        if (e.rays == rays && e.count == num_rays && e.cost && e.history_tiles >= (num_rays + 31) / 32) {
+            const int tiles = std::min(capacity, (num_rays + 31) / 32);
+            HGB_CUDA(cudaDeviceSynchronize());
+            HGB_CUDA(cudaMemcpy(out, e.cost, sizeof(unsigned short) * size_t(tiles), cudaMemcpyDeviceToHost));
+            return tiles;
+        }
+    return 0;
+}
+
 } // namespace hagrid
+
+extern "C" __attribute__((visibility("default"))) int hgb_debug_tile_costs(const void* rays, int num_rays, unsigned short* out, int capacity) {
+    return hagrid::debug_tile_costs(rays, num_rays, out, capacity);
+}
 
 #ifdef HGB_TILE_TRACE
 extern "C" __attribute__((visibility("default"))) int hgb_debug_tile_trace(long long* out) {

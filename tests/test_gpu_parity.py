@@ -565,6 +565,81 @@ def test_a_reused_ray_buffer_may_change_its_character(lib, sponza):
         sc.device_free(d_rays); sc.device_free(d_hits)
 
 
+TILE_HISTORY_SETTINGS = [            # tile_order (cost classes, bits), tile_split (tiles), tile_split_log, tile_split_share (%)
+    (8, 256, 2, 50),                 # the defaults
+    (8, 1024, 5, 0),                 # the thousand most expensive tiles as 32 single rays each
+    (4, 64, 1, 0),
+    (12, 256, 3, 25),
+    (1, 0, 2, 50),                   # two classes, nothing in parts
+    (0, 0, 2, 50),                   # off: buffer order
+]
+
+
+def _set_tile_history(lib, order, split, split_log, share):
+    lib.set_option("tile_order", order); lib.set_option("tile_split", split)
+    lib.set_option("tile_split_log", split_log); lib.set_option("tile_split_share", share)
+
+
+def test_tiles_handed_out_by_their_history_give_the_same_hits(lib, sponza, sponza_reference):
+    """The tile kernel times its tiles and hands them out longest first on later launches of the same buffer, the most
+    expensive ones in parts (TileHistory in ray_traverse.cu). Neither may change a hit: the bench's C2 buffers, launch
+    after launch under several settings, prim ids, t and step counts bit-identical to the reference's every time --
+    also when the rays in the buffer change under a history made from other rays, and for a raster whose height is no
+    multiple of the tile height traced by the tile kernel although it is small."""
+    tris, sc, _ = sponza
+    sc.setup_traversal()
+    R = sponza_reference
+    n = R["views"]["default"].shape[0]
+    d_rays, d_hits = sc.device_alloc(n * 32), sc.device_alloc(n * 16)
+    try:
+        for setting in TILE_HISTORY_SETTINGS:
+            _set_tile_history(lib, *setting)
+            for launch in range(6):
+                name = ("default", "long")[launch % 3 == 2]          # every third launch: other rays, same buffer
+                sc.to_device(d_rays, R["views"][name])
+                for mode, want in zip((HIT_PRIM_ID, HIT_STEPS), R["want"][name]):
+                    sc.traverse(d_rays, d_hits, n, mode)
+                    got = sc.to_host(np.empty(n, dtype=want.dtype), d_hits)
+                    assert _bit_equal(got, want), (setting, launch, name, mode)
+        # a small ragged raster through the tile kernel
+        small = scenes.default_view(tris, 648, 357)
+        lib.set_option("traverse_variant", 0)
+        want = sc.trace(small, HIT_PRIM_ID)
+        lib.set_option("traverse_variant", 4)
+        m = small.shape[0]
+        sc.to_device(d_rays, small)
+        for setting in TILE_HISTORY_SETTINGS[:4]:
+            _set_tile_history(lib, *setting)
+            for launch in range(5):
+                sc.traverse(d_rays, d_hits, m, HIT_PRIM_ID)
+                got = sc.to_host(np.empty(m, dtype=want.dtype), d_hits)
+                assert _bit_equal(got, want), (setting, launch)
+        # more buffers than the library remembers (4), of different sizes, taking turns: a history is never carried
+        # over to another buffer
+        _set_tile_history(lib, 8, 256, 2, 0)
+        frames = [scenes.default_view(tris, 648, h) for h in (96, 357, 200, 64, 300, 128)]
+        lib.set_option("traverse_variant", 0)
+        wants = [sc.trace(f, HIT_PRIM_ID) for f in frames]
+        lib.set_option("traverse_variant", 4)
+        bufs = [sc.device_alloc(f.shape[0] * 32) for f in frames]
+        try:
+            for b, f in zip(bufs, frames):
+                sc.to_device(b, f)
+            for round_ in range(3):
+                for b, f, want in zip(bufs, frames, wants):
+                    for launch in range(3):
+                        sc.traverse(b, d_hits, f.shape[0], HIT_PRIM_ID)
+                        got = sc.to_host(np.empty(f.shape[0], dtype=want.dtype), d_hits)
+                        assert _bit_equal(got, want), (round_, f.shape[0], launch)
+        finally:
+            for b in bufs:
+                sc.device_free(b)
+    finally:
+        lib.set_option("traverse_variant", 3)
+        _set_tile_history(lib, *TILE_HISTORY_SETTINGS[0])
+        sc.device_free(d_rays); sc.device_free(d_hits)
+
+
 def test_tracing_a_grid_without_its_setup_is_an_error(lib):
     """hgb_setup_traversal must follow every change of a scene's grid (the reference's call order,
     src/main.cpp:536-549; its constants are per process, src/traverse.cu:7-12): the C ABI refuses to trace a
