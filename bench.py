@@ -493,10 +493,13 @@ def bench_single_gpu(ctx: Ctx, lib, args, reference, local_rank, affinity):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": ("traverse_pid<Cell, Tri>" if reference else "traverse_tiles<Cell, 1>") + " (the only kernel of a step)",
+                     "kernel": "traverse_pid<Cell, Tri> (the only kernel of a step)" if reference else
+                               "traverse_tiles<Cell, 1> (the only kernel of a step; every 16th step times its tiles and is followed, on a side "
+                               "stream, by the 8 small kernels that sort the tiles by cost for the steps after it)",
                      "algorithmic_bytes_per_launch": algo_bytes,
-                     "note": "gather kernel bound by instruction issue and dependent-load latency (ncu: 71 % of peak issue rate, 22.6 of 32 lanes "
-                             "active, DRAM 7 % of peak): compulsory HBM traffic is 48 B/ray + the part of the scene the view touches; "
+                     "note": "gather kernel bound by instruction issue and dependent-load latency (ncu, profiles/r02b_traverse_primary_metrics.csv: "
+                             "76 % of peak issue rate, 23.0 of 32 lanes active, DRAM 6 % of peak): compulsory HBM traffic is 48 B/ray + the part "
+                             "of the scene the view touches; "
                              "traffic = dram read + write bytes of one launch under ncu with caches flushed (profiles/r02_traverse_dram.json); "
                              "see DESIGN.md section 5"},
         "build_ms": {"mean": round(float(build_ms.mean()), 3), "median": round(float(np.median(build_ms)), 3),

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "hgb_last_error": (C.c_char_p, []),
     "hgb_device_count": (C.c_int, []),
     "hgb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "hgb_tile_costs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "hgb_scene_create": (C.c_void_p, [C.c_int, C.c_int]),
     "hgb_scene_destroy": (None, [C.c_void_p]),
     "hgb_scene_set_tris": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

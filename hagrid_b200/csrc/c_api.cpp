@@ -55,6 +55,7 @@ void prim_reduce(MemManager& mem, const void* in, int n, int op, void* out);
 int prim_partition(MemManager& mem, const int* in, const int* flags, int n, int* out);
 void prim_sort_pairs(MemManager& mem, int* keys, int* vals, int n, int bits);
 bool set_traversal_option(const char* key, int value);
+int debug_tile_costs(const void* rays, int num_rays, unsigned short* out, int capacity);
 unsigned long long kernel_launch_count();
 void trim_device_pool();
 #endif
@@ -180,6 +181,16 @@ int hgb_set_option(const char* key, int value) {
     return 0;
 #else
     return set_traversal_option(key, value) ? 0 : fail("set_option: unknown key");
+#endif
+}
+
+int hgb_tile_costs(const void* dev_rays, int num_rays, unsigned short* host_costs, int capacity) {
+#ifdef HGB_REFERENCE_BUILD
+    (void)dev_rays; (void)num_rays; (void)host_costs; (void)capacity;
+    return 0;
+#else
+    if (!dev_rays || !host_costs || num_rays <= 0 || capacity <= 0) return 0;
+    return debug_tile_costs(dev_rays, num_rays, host_costs, capacity);
 #endif
 }
 

@@ -898,8 +898,12 @@ std::atomic<int> g_two_wave_chunks{1};
 // incoherent buffers smaller than this many rays are traced one thread per ray: the persistent voting warps pay off from
 // about 600 K rays (tools/gpu_incoherent_threshold.py: 259 K rays of the C5 second wave 0.363 vs 0.432 ms, 1 M rays 0.785 vs 0.722)
 std::atomic<int> g_vote_min_rays{768 << 10};
-// rasters smaller than this many rays are traced one thread per ray (re-tiled): a small launch does not fill the resident warps
-std::atomic<int> g_tile_min_rays{1280 << 10};      // profiles/r02_traverse_experiments.md: half a 1920x1080 frame is on the line
+// rasters smaller than this many rays are traced one thread per ray (re-tiled): a small launch does not fill the resident
+// warps. Two lines (profiles/r02_traverse_experiments.md): a launch that has a ticket list for its buffer, or is about to
+// time its tiles for one, wins down to an eighth of a 1920x1080 frame (C2 1 M / 518 K / 259 K rays: 0.083 / 0.053 / 0.046 ms
+// against 0.098 / 0.067 / 0.049 one thread per ray); without a list half a frame is on the line.
+std::atomic<int> g_tile_min_rays{128 << 10};
+std::atomic<int> g_tile_cold_min_rays{1280 << 10};
 
 int traverse_variant() {
     int v = g_variant.load();
@@ -1109,7 +1113,7 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
         if (variant == 3) {
             // small buffers do not fill the resident-warp kernels (7 104 warps on 148 SMs): one thread per ray then
             if (buf->cls == 0) variant = num_rays < g_vote_min_rays.load() ? 0 : 1;
-            else               variant = num_rays < g_tile_min_rays.load() ? 2 : 4;
+            else               variant = num_rays < (g_tile_order_bits.load() > 0 ? g_tile_min_rays : g_tile_cold_min_rays).load() ? 2 : 4;
         }
         if (variant == 4 && buf->cls > 0) {
             feedback = buf->feedback_dev;
@@ -1142,7 +1146,11 @@ void launch(const Grid& grid, const CellT* cells, const Tri* tris, const Ray* ra
     TileHistory history{nullptr, nullptr, 0, 0};
     bool timed = false;
     const int order_bits = g_tile_order_bits.load();
-    if (variant == 4 && buf && buf->cls > 0 && order_bits > 0) timed = tile_history(st, *buf, num_rays, history, 0);
+    if (variant == 4 && buf && buf->cls > 0 && order_bits > 0) {
+        timed = tile_history(st, *buf, num_rays, history, 0);
+        // the one launch of a small buffer that neither has a list nor makes one (the second on the buffer)
+        if (traverse_variant() == 3 && !timed && !history.tickets && num_rays < g_tile_cold_min_rays.load()) { variant = 2; feedback = nullptr; }
+    }
     enqueue<CellT, kPrimId>(grid, cells, tris, rays, hits, num_rays, variant, tiled && buf ? buf->layout : nullptr, 0,
                             st.vote_counter, st.tiles, st.num_sms, 0, feedback, order, history);
     if (timed) order_tiles(st, *buf, num_rays, order_bits, 0);
@@ -1346,7 +1354,8 @@ void launch_two_waves(const Grid& grid, const CellT* cells, const Tri* tris, int
         cudaStream_t run = st.streams[2 + (c & 1)];
         int first = forced, second = forced;
         if (forced == 3) {
-            first = width > 0 ? (count < g_tile_min_rays.load() ? 2 : 4) : (count < g_vote_min_rays.load() ? 0 : 1);
+            const bool listed = count == num_rays && g_tile_order_bits.load() > 0;      // see below: a frame in one piece
+            first = width > 0 ? (count < (listed ? g_tile_min_rays : g_tile_cold_min_rays).load() ? 2 : 4) : (count < g_vote_min_rays.load() ? 0 : 1);
             second = count < g_vote_min_rays.load() ? 0 : 1;
         } else if (forced == 2 || forced == 4) {
             if (width <= 0) first = 0;
@@ -1456,7 +1465,8 @@ bool set_traversal_option(const char* key, int value) {
     if (!std::strcmp(key, "tile_split_share")) { g_tile_split_share.store(std::max(0, value)); g_tile_history_epoch++; return true; }
     if (!std::strcmp(key, "two_wave_chunks")) { g_two_wave_chunks.store(value > 0 ? min(value, 16) : 1); return true; }
     if (!std::strcmp(key, "vote_min_rays")) { g_vote_min_rays.store(value >= 0 ? value : (768 << 10)); return true; }
-    if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (1280 << 10)); return true; }
+    if (!std::strcmp(key, "tile_min_rays")) { g_tile_min_rays.store(value >= 0 ? value : (128 << 10)); return true; }
+    if (!std::strcmp(key, "tile_cold_min_rays")) { g_tile_cold_min_rays.store(value >= 0 ? value : (1280 << 10)); return true; }
     return false;
 }
 
@@ -1515,10 +1525,6 @@ int debug_tile_costs(const void* rays, int num_rays, unsigned short* out, int ca
 }
 
 } // namespace hagrid
-
-extern "C" __attribute__((visibility("default"))) int hgb_debug_tile_costs(const void* rays, int num_rays, unsigned short* out, int capacity) {
-    return hagrid::debug_tile_costs(rays, num_rays, out, capacity);
-}
 
 #ifdef HGB_TILE_TRACE
 extern "C" __attribute__((visibility("default"))) int hgb_debug_tile_trace(long long* out) {

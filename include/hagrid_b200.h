@@ -81,8 +81,25 @@ HGB_API int  hgb_device_count(void);
  *                            ray re-tiled 8x4 when the buffer is a raster, 4 = resident warps pulling 8x4 tiles,
  *                            3 = automatic (default: 4 for rasters, 1 otherwise)
  *   "host_frame_chunk_rays"  rays per full-size chunk of hgb_traverse_grid_host's pipeline
- * Returns 0 when the key is known. */
+ *   "tile_min_rays"          rasters below this many rays go to variant 2 instead of 4 under "automatic" (default
+ *                            128 K); "tile_cold_min_rays" is the same line for launches without a ticket list
+ *                            ("tile_order" 0, or the second launch on a buffer; default 1280 K)
+ *   "vote_min_rays"          incoherent buffers below this many rays go to variant 0 instead of 1
+ *   "tile_order"             variant 4 hands the tiles of a ray buffer out by what they cost on earlier launches
+ *                            of the same buffer, longest first, in 2^value cost classes (default 8; 0 = buffer order)
+ *   "tile_split"             ... and up to this many of the most expensive tiles in parts (default 256; 0 = none)
+ *   "tile_split_log"         ... 2^value parts per tile (default 2; at most 5 = single rays)
+ *   "tile_split_share"       ... only tiles that cost at least value % of one resident warp's share of the launch
+ *                            (default 50)
+ *   "two_wave_chunks"        pieces hgb_trace_two_waves cuts a frame into (default 1)
+ *   "ray_sort"               1 = bin incoherent rays by octant and entry cell before tracing (default 0)
+ * None of them can change a hit. Returns 0 when the key is known. */
 HGB_API int  hgb_set_option(const char* key, int value);
+/* Diagnosis: the per-tile times variant 4 last recorded for the device ray buffer (`dev_rays`, `num_rays`), in SM
+ * clock ticks / 64 per tile of 32 rays (8x4 pixels of a raster), copied to `host_costs` (at most `capacity`
+ * entries). Returns the number of entries written, 0 when nothing is recorded for that buffer (always 0 in the
+ * reference build). */
+HGB_API int  hgb_tile_costs(const void* dev_rays, int num_rays, unsigned short* host_costs, int capacity);
 
 /* Scene life cycle: MemManager(keep) + Tri upload, main.cpp:471-478. */
 HGB_API hgb_scene* hgb_scene_create(int device, int keep_alive);

@@ -180,7 +180,9 @@ while time.time() < t_end:
             for mode in (HIT_STEPS, HIT_PRIM_ID):
                 ha = a.trace(r, mode)
                 # 3 = the library's own choice (small buffers: one thread per ray); the others force each kernel in turn
-                for variant in (3, 0, 1, 2, 4):
+                # (the tile kernel four times in a row: from its third launch on a buffer it hands the tiles out by what
+                # they cost before, the most expensive ones in parts)
+                for variant in (3, 0, 1, 2, 4, 4, 4, 4):
                     mine.set_option("traverse_variant", variant)
                     hb = b.trace(r, mode)
                     buffers_checked += 1

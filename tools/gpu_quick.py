@@ -20,6 +20,11 @@ if "c2" in wanted:
     sr, sm = g.scene_pair(tris)
     g.compare_buffer("c2_primary", sr, sm, scenes.default_view(tris), settings, 50)
     g.compare_buffer("c2_long", sr, sm, scenes.default_view(tris, along_long_axis=True), settings, 30)
+    if "shards" in wanted:
+        primary = scenes.default_view(tris)
+        for world in (2, 4, 8):
+            idx = sharding.interleaved_bands(primary.shape[0], 0, world, sharding.raster_granule(1920))
+            g.compare_buffer(f"c2_primary_1of{world}", sr, sm, np.ascontiguousarray(primary[idx]), settings, 30)
     sr.close(); sm.close()
 if "c3" in wanted:
     tris = scenes.sponza262k()
@@ -32,8 +37,9 @@ if "c5" in wanted or "c5b" in wanted:
     primary = scenes.default_view(tris)
     if "c5" in wanted:
         g.compare_buffer("c5_primary", sr, sm, primary, settings, 30)
-        idx = sharding.interleaved_bands(primary.shape[0], 0, 8, sharding.raster_granule(1920))
-        g.compare_buffer("c5_primary_1of8", sr, sm, np.ascontiguousarray(primary[idx]), settings, 30)
+        for world in (2, 4, 8):
+            idx = sharding.interleaved_bands(primary.shape[0], 0, world, sharding.raster_granule(1920))
+            g.compare_buffer(f"c5_primary_1of{world}", sr, sm, np.ascontiguousarray(primary[idx]), settings, 30)
     if "c5b" in wanted:
         first = sm.trace(primary, HIT_PRIM_ID)
         bounce = scenes.bounce_rays(tris, primary, first["id"], first["t"])

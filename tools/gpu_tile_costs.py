@@ -8,8 +8,6 @@ sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tools"))
 from hagrid_b200 import HIT_PRIM_ID, Library, Scene, scenes
 
 lib = Library()
-lib.dll.hgb_debug_tile_costs.restype = C.c_int
-lib.dll.hgb_debug_tile_costs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
 out = {}
 for tag, tris in (("c2", scenes.sponza262k()), ("c5", scenes.sanmiguel7p8m())):
     scene = Scene(tris, keep_alive=True, lib=lib); scene.build_all(0.15, 3.0, 0.995, 3, False); scene.setup_traversal()
@@ -24,7 +22,7 @@ for tag, tris in (("c2", scenes.sponza262k()), ("c5", scenes.sanmiguel7p8m())):
             scene.traverse(d_rays, d_hits, n, HIT_PRIM_ID)
         torch.cuda.synchronize()
         cost = np.zeros((n + 31) // 32, dtype=np.uint16)
-        got = lib.dll.hgb_debug_tile_costs(C.c_void_p(d_rays.data_ptr()), n, C.c_void_p(cost.ctypes.data), cost.size)
+        got = lib.dll.hgb_tile_costs(C.c_void_p(d_rays.data_ptr()), n, C.c_void_p(cost.ctypes.data), cost.size)
         assert got == cost.size, got
         mhz = 1920      # SM clock under load on this pool (bench.py's clocks line)
         us = cost.astype(np.float64) * 64 / mhz
