@@ -55,6 +55,7 @@ void prim_reduce(MemManager& mem, const void* in, int n, int op, void* out);
 int prim_partition(MemManager& mem, const int* in, const int* flags, int n, int* out);
 void prim_sort_pairs(MemManager& mem, int* keys, int* vals, int n, int bits);
 bool set_traversal_option(const char* key, int value);
+bool set_merge_option(const char* key, int value);
 int debug_tile_costs(const void* rays, int num_rays, unsigned short* out, int capacity);
 unsigned long long kernel_launch_count();
 void trim_device_pool();
@@ -180,7 +181,7 @@ int hgb_set_option(const char* key, int value) {
     (void)value;
     return 0;
 #else
-    return set_traversal_option(key, value) ? 0 : fail("set_option: unknown key");
+    return set_traversal_option(key, value) || set_merge_option(key, value) ? 0 : fail("set_option: unknown key");
 #endif
 }
 

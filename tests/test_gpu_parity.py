@@ -356,6 +356,29 @@ def test_build_is_deterministic(lib):
     a.close(); b.close()
 
 
+def test_merge_in_one_launch_and_pass_by_pass_give_the_same_grid(lib, ref_lib):
+    """merge_grid runs all its rounds in one cooperative launch on grids of up to 512 K cells and one launch per kernel and
+    pass above that: the same grid either way, and the reference's, on scenes of both sizes with either path forced;
+    alpha values that end the loop after one round and after many."""
+    cases = [(scenes.sponza262k(), 0.15, 3.0, 0.995), (scenes.hairball(60000, seed=5), 0.12, 2.4, 0.995),
+             (scenes.hairball(60000, seed=5), 0.12, 2.4, 0.5), (scenes.hairball(3000, seed=9), 0.12, 2.4, 1.0)]
+    try:
+        for tris, td, sd, alpha in cases:
+            r = Scene(tris, lib=ref_lib)
+            r.build_grid(td, sd); r.merge_grid(alpha)
+            want = dump(r)
+            r.close()
+            for limit in (0, 1 << 30):
+                lib.set_option("merge_one_launch_max_cells", limit)
+                m = Scene(tris, lib=lib)
+                m.build_grid(td, sd); m.merge_grid(alpha)
+                info, arrays = dump(m)
+                assert grid_diff(info, arrays, (want[0],) + want[1]) == [], (tris.shape[0], alpha, limit)
+                m.close()
+    finally:
+        lib.set_option("merge_one_launch_max_cells", -1)
+
+
 # ----------------------------------------------------------------------------- edge cases
 def test_ragged_and_empty_ray_buffers(lib):
     g = Golden("cornell32")
