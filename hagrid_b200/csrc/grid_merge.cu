@@ -490,16 +490,17 @@ __global__ void __launch_bounds__(kRoundBlock, kRoundBlocksPerSm) merge_rounds(c
     if (blockIdx.x == 0 && threadIdx.x == 0) *A.passes_done = pass;
 }
 
-// grids of up to this many cells are merged in one launch (0: never). tools/gpu_merge_threshold.py: C2 (234 K cells) builds
-// in 2.56 instead of 2.69 ms; C4 (7.1 M cells) in 19.0 instead of 12.7 ms, C5 (13.7 M) in 55 instead of 34 ms -- big
-// grids want every SM full of threads in each phase, not 1 024 per SM and a barrier.
-std::atomic<int> g_one_launch_max_cells{512 << 10};
+// grids of up to this many cells (before merging) are merged in one launch (0: never). tools/gpu_merge_threshold.py, whole
+// builds: 46 K cells 1.14 -> 1.01 ms, 167 K 1.24 -> 1.10, 521 K 1.49 -> 1.41, C2 (551 K) 2.70 -> 2.59; 1.29 M 2.10 -> 2.19,
+// 3.1 M 3.44 -> 4.16, C4 (7.1 M after merging) 12.7 -> 19.0, C5 34 -> 55 -- big grids want every SM full of threads in each
+// phase, not 1 024 per SM and a barrier.
+std::atomic<int> g_one_launch_max_cells{768 << 10};
 
 } // namespace
 
 bool set_merge_option(const char* key, int value) {
     if (std::strcmp(key, "merge_one_launch_max_cells") != 0) return false;
-    g_one_launch_max_cells.store(value >= 0 ? value : (512 << 10));
+    g_one_launch_max_cells.store(value >= 0 ? value : (768 << 10));
     return true;
 }
 

@@ -94,7 +94,7 @@ HGB_API int  hgb_device_count(void);
  *   "two_wave_chunks"        pieces hgb_trace_two_waves cuts a frame into (default 1)
  *   "ray_sort"               1 = bin incoherent rays by octant and entry cell before tracing (default 0)
  *   "merge_one_launch_max_cells"  hgb_merge_grid runs all its passes in one cooperative launch on grids of up to this
- *                            many cells (default 512 K; 0 = one launch per kernel and pass)
+ *                            many cells before merging (default 768 K; 0 = one launch per kernel and pass)
  * None of them can change a hit. Returns 0 when the key is known. */
 HGB_API int  hgb_set_option(const char* key, int value);
 /* Diagnosis: the per-tile times variant 4 last recorded for the device ray buffer (`dev_rays`, `num_rays`), in SM

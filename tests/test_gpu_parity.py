@@ -357,7 +357,7 @@ def test_build_is_deterministic(lib):
 
 
 def test_merge_in_one_launch_and_pass_by_pass_give_the_same_grid(lib, ref_lib):
-    """merge_grid runs all its rounds in one cooperative launch on grids of up to 512 K cells and one launch per kernel and
+    """merge_grid runs all its rounds in one cooperative launch on grids of up to 768 K cells and one launch per kernel and
     pass above that: the same grid either way, and the reference's, on scenes of both sizes with either path forced;
     alpha values that end the loop after one round and after many."""
     cases = [(scenes.sponza262k(), 0.15, 3.0, 0.995), (scenes.hairball(60000, seed=5), 0.12, 2.4, 0.995),
