@@ -533,12 +533,18 @@ void merge_grid(MemManager& mem, Grid& grid, float alpha) {
     P.shift = grid.shift;
     P.cell_x = cell_size.x; P.cell_y = cell_size.y; P.cell_z = cell_size.z;
 
-    if (alpha > 0 && grid.num_cells > 0 && grid.num_cells <= g_one_launch_max_cells.load()) {
-        static int blocks_per_sm = 0;           // what fits of this kernel (the same on every device of one kind)
-        if (!blocks_per_sm) {
-            HGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds, kRoundBlock, 0));
-            blocks_per_sm = std::max(1, std::min(blocks_per_sm, kRoundBlocksPerSm));
-        }
+    // blocks of merge_rounds that fit an SM (the same on every device of one kind); 0: no cooperative launches here
+    static std::atomic<int> resident{-1};
+    int blocks_per_sm = resident.load();
+    if (blocks_per_sm < 0) {
+        int dev = 0, cooperative = 0;
+        HGB_CUDA(cudaGetDevice(&dev));
+        HGB_CUDA(cudaDeviceGetAttribute(&cooperative, cudaDevAttrCooperativeLaunch, dev));
+        HGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, merge_rounds, kRoundBlock, 0));
+        blocks_per_sm = cooperative ? std::max(0, std::min(blocks_per_sm, kRoundBlocksPerSm)) : 0;
+        resident.store(blocks_per_sm);
+    }
+    if (alpha > 0 && grid.num_cells > 0 && grid.num_cells <= g_one_launch_max_cells.load() && blocks_per_sm > 0) {
         const int blocks = std::min(sm_count() * blocks_per_sm, (grid.num_cells + kRoundBlock - 1) / kRoundBlock);
         // block sums and the pass count share the scan scratch (its look-back words are not used on this path)
         RoundArgs A;
