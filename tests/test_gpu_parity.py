@@ -663,6 +663,30 @@ def test_tiles_handed_out_by_their_history_give_the_same_hits(lib, sponza, sponz
         sc.device_free(d_rays); sc.device_free(d_hits)
 
 
+def test_tile_costs_can_be_read_back(lib, sponza):
+    """hgb_tile_costs: the per-tile times the tile kernel records for its ticket list -- nothing for a buffer that was
+    never traced, one entry per 32 rays afterwards, expensive tiles where the rays are long."""
+    import ctypes as C
+    tris, sc, _ = sponza
+    sc.setup_traversal()
+    rays = scenes.default_view(tris)
+    n = rays.shape[0]
+    tiles = (n + 31) // 32
+    d_rays, d_hits = sc.device_alloc(n * 32), sc.device_alloc(n * 16)
+    cost = np.zeros(tiles, dtype=np.uint16)
+    try:
+        sc.to_device(d_rays, rays)
+        assert lib.dll.hgb_tile_costs(C.c_void_p(d_hits), n, C.c_void_p(cost.ctypes.data), tiles) == 0        # not a ray buffer it knows
+        for _ in range(3):
+            sc.traverse(d_rays, d_hits, n, HIT_PRIM_ID)
+        assert lib.dll.hgb_tile_costs(C.c_void_p(d_rays), n, C.c_void_p(cost.ctypes.data), tiles) == tiles
+        assert (cost > 0).all() and cost.max() > 3 * np.median(cost)
+        assert lib.dll.hgb_tile_costs(C.c_void_p(d_rays), n, C.c_void_p(cost.ctypes.data), 100) == 100        # capacity respected
+        assert lib.dll.hgb_tile_costs(None, n, C.c_void_p(cost.ctypes.data), tiles) == 0
+    finally:
+        sc.device_free(d_rays); sc.device_free(d_hits)
+
+
 def test_tracing_a_grid_without_its_setup_is_an_error(lib):
     """hgb_setup_traversal must follow every change of a scene's grid (the reference's call order,
     src/main.cpp:536-549; its constants are per process, src/traverse.cu:7-12): the C ABI refuses to trace a
