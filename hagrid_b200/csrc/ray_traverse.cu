@@ -680,7 +680,10 @@ constexpr int kBlockThreads = 128;
 constexpr int kVoteBlock = 32;          // rays reserved per atomic
 constexpr int kVoteRefillMinLanes = 4;
 constexpr int kVoteTurn = 3;            // references a lane tests per triangle turn
-constexpr int kVoteBlocksPerSm = 10;    // <= 51 registers
+#ifndef HGB_VOTE_BLOCKS
+#define HGB_VOTE_BLOCKS 10
+#endif
+constexpr int kVoteBlocksPerSm = HGB_VOTE_BLOCKS;    // 10: <= 51 registers
 
 template <typename CellT, bool kPrimId>
 __global__ void __launch_bounds__(kBlockThreads, kVoteBlocksPerSm)
