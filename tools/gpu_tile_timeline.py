@@ -15,12 +15,13 @@ sc = Scene(tris, keep_alive=True, lib=lib); sc.build_all(0.15, 3.0); sc.setup_tr
 d_rays = torch.from_numpy(rays.view(np.float32).reshape(n, 8)).cuda(); d_hits = torch.empty((n, 4), dtype=torch.float32, device="cuda")
 for k, v in (a.split("=") for a in sys.argv[2:]):
     lib.set_option(k, int(v))
-for rep in range(4):
+for rep in range(6):          # from the third launch on the tiles are handed out by the ticket list (unless tile_order=0)
     flush.zero_(); a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
     a.record(); sc.traverse(d_rays, d_hits, n, HIT_PRIM_ID); b.record(); torch.cuda.synchronize()
     buf = np.zeros(3 * 8192, dtype=np.int64)
     assert lib.dll.hgb_debug_tile_trace(C.c_void_p(buf.ctypes.data)) == 0
-    t = buf.reshape(-1, 3)[:5920]
+    t = buf.reshape(-1, 3)
+    t = t[t[:, 1] > 0]                              # the warps of this launch (148 SMs x 12 blocks x 4)
     t0 = t[:, 0].min()
     start, end, cnt = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, t[:, 2]
     q = lambda x, p: float(np.percentile(x, p))
