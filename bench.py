@@ -395,6 +395,18 @@ def bench_single_gpu(ctx: Ctx, lib, args, reference, local_rank, affinity):
     step_ms = ctx.timed(lambda: scene.traverse(d_rays, d_hits, n, HIT_PRIM_ID), args.steps, args.warmup)
     launches = lib.kernel_launches() - launches0
     hits = d_hits.cpu().numpy().view(HIT).reshape(-1)
+    # the same steps with the tiles handed out in buffer order (what the first two launches on a new ray buffer cost:
+    # from the third on the kernel orders its tiles by what they cost before) -- reported beside the headline
+    unordered = None
+    if not reference:
+        lib.set_option("tile_order", 0)
+        u_steps = max(3, min(args.steps, 50))
+        u_ms = ctx.timed(lambda: scene.traverse(d_rays, d_hits, n, HIT_PRIM_ID), u_steps, 3)
+        lib.set_option("tile_order", 8)
+        unordered = {"value": round(n * u_steps / (1000.0 * float(u_ms.sum())), 1), "unit": "Mrays/s",
+                     "ms_per_step": round(float(u_ms.mean()), 5), "steps": u_steps,
+                     "hits_identical": bool(np.array_equal(d_hits.cpu().numpy().view(HIT).reshape(-1), hits)),
+                     "what": "hgb_set_option('tile_order', 0): tiles in buffer order, no use of earlier launches"}
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
     h_rays = torch.from_numpy(rays.view(np.float32).reshape(n, 8)).pin_memory()
@@ -482,13 +494,17 @@ def bench_single_gpu(ctx: Ctx, lib, args, reference, local_rank, affinity):
         "config": {"workload": C2_WORKLOAD, "rays_per_step_per_gpu": n,
                    "grid": {k: info[k] for k in ("dims", "shift", "num_cells", "num_entries", "num_refs")},
                    "l2": "256 MiB memset between steps (L2 flushed); scene+rays+hits = %.1f MB" % (algo_bytes / 1e6),
-                   "timing": "CUDA event pair per step on the legacy default stream, sum over steps"},
+                   "timing": "CUDA event pair per step on the legacy default stream, sum over steps",
+                   "tile_order": "steps trace the same ray buffer: from the third launch on the tile kernel hands out the buffer's tiles by what "
+                                 "they cost on earlier launches (all rays traced every step, hits unchanged); `tiles_in_buffer_order` is the "
+                                 "same measurement without it"},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 16 * n,
                 "ms_per_step": round(e2e_total / e2e_steps, 4), "steps": e2e_steps,
                 "hits_match_device_path": bool(np.array_equal(e2e_hits["id"], hits["id"]) and np.array_equal(e2e_hits["t"], hits["t"])),
                 "hits_crc": crc_of(e2e_hits),
                 "api": "hgb_traverse_grid_host (pinned host buffers)", "host_affinity_rank0": affinity},
         "hits_crc": crc_of(hits),
+        "tiles_in_buffer_order": unordered,
         "gpu_launches": int(launches) if not reference else 0,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
