@@ -939,9 +939,10 @@ std::atomic<int> g_ray_sort{0};
 
 // "tile_order": cost classes (bits, 1 ... 8) the tiles of a raster are handed out by; 0 = always buffer order
 std::atomic<int> g_tile_order_bits{8};
-// "tile_split" / "tile_split_log": how many of the most expensive tiles are handed out in 2^tile_split_log parts
+// "tile_split" / "tile_split_log" / "tile_split_share": how many of the most expensive tiles are handed out in 2^tile_split_log
+// parts, if such a tile alone costs at least that many percent of one resident warp's share of the launch
 std::atomic<int> g_tile_split{256}, g_tile_split_log{2}, g_tile_split_share{50};
-std::atomic<int> g_tile_history_epoch{0};      // bumped when one of the three changes: what was learnt under other settings is dropped
+std::atomic<int> g_tile_history_epoch{0};      // bumped when one of these options changes: what was learnt under other settings is dropped
 
 /// What the next launch of traverse_tiles on `buf` gets (TileHistory): the newest order -- the one made from timed
 /// launch k is used from launch k + 2 on, so that it is made while launch k + 1 runs and nobody waits for it -- and a
